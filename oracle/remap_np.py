@@ -1,0 +1,142 @@
+"""ORACLE (test infrastructure, never shipped, never on the product path).
+
+numpy restatement of ``cv2.remap(src, map32FC2, None, interp, dst, BORDER_CONSTANT, fill)`` as the
+reference calls it at ``tobac_flow/convolve.py:65-84`` and ``tobac_flow/utils/flow_utils.py:90-98``.
+
+The arithmetic lives in OpenCV (not vendored in /root/reference; image has 4.13.0).  Restated from
+opencv/modules/imgproc/src/imgwarp.cpp (remap, remapNearest, remapBilinear, remapBicubic,
+interpolateLinear/Cubic, initInterTab2D):
+
+* float maps are converted to fixed point: s = cvRound(coord * 32) (round half even), integer part
+  s >> 5, fraction (s & 31) / 32;  nearest uses cvRound(coord) with no sub-pixel part;
+* weights are fp32 table entries wy[k1] * wx[k2]; accumulation in fp32 for fp32 sources and fp64 for
+  fp64 sources, left to right;
+* BORDER_CONSTANT is evaluated per tap, so an out-of-image tap contributes fill*w even when w == 0
+  (with fill = NaN the last row/column of a zero-flow linear warp is NaN).
+
+Pinned against cv2 in ``tests/test_oracle_remap.py`` and against the five ``warp_flow`` cases of the
+reference's ``tests/test_flow.py:94-161``.
+"""
+import numpy as np
+
+F32 = np.float32
+
+INTERP_CODES = {"nearest": 0, "linear": 1, "cubic": 2, "lanczos": 3}
+
+
+def _round_half_even_i64(v: np.ndarray) -> np.ndarray:
+    with np.errstate(invalid="ignore"):
+        r = np.rint(v)
+    bad = ~np.isfinite(r) | (np.abs(r) > 2.0e9)
+    r = np.where(bad, -2147483648.0, r)  # cvRound of NaN/inf/overflow -> INT_MIN ("integer indefinite")
+    return r.astype(np.int64)
+
+
+def _sat_short(v: np.ndarray) -> np.ndarray:
+    return np.clip(v, -32768, 32767)
+
+
+def _cubic_coeffs(frac_idx: np.ndarray) -> np.ndarray:
+    """interpolateCubic on x = idx/32, fp32 arithmetic, A = -0.75."""
+    A = F32(-0.75)
+    x = (frac_idx.astype(F32) * F32(1.0 / 32.0)).astype(F32)
+    one = F32(1)
+    c0 = ((A * (x + one) - F32(5) * A) * (x + one) + F32(8) * A) * (x + one) - F32(4) * A
+    c1 = ((A + F32(2)) * x - (A + F32(3))) * x * x + one
+    omx = one - x
+    c2 = ((A + F32(2)) * omx - (A + F32(3))) * omx * omx + one
+    c3 = one - c0 - c1 - c2
+    return np.stack([c0, c1, c2, c3], -1).astype(F32)
+
+
+def remap(src: np.ndarray, mapx: np.ndarray, mapy: np.ndarray, method: str = "linear",
+          fill_value=np.nan) -> np.ndarray:
+    """Gather ``src`` (H, W) at float32 positions (mapx, mapy) (any common shape)."""
+    if method not in INTERP_CODES:
+        raise ValueError(f"method must be one of {list(INTERP_CODES)}")
+    src = np.asarray(src)
+    H, W = src.shape
+    mapx = np.asarray(mapx, dtype=F32)
+    mapy = np.asarray(mapy, dtype=F32)
+    if src.dtype == np.float64:
+        wt = np.float64
+    elif src.dtype == np.float32:
+        wt = F32
+    else:
+        if method != "nearest":
+            raise TypeError("cv2.remap: only nearest interpolation supports integer sources")
+        wt = src.dtype
+    with np.errstate(invalid="ignore", over="ignore"):
+        fill = np.array(fill_value).astype(src.dtype)
+
+    if method == "nearest":
+        ix = _sat_short(_round_half_even_i64(mapx))
+        iy = _sat_short(_round_half_even_i64(mapy))
+        inb = (ix >= 0) & (ix < W) & (iy >= 0) & (iy < H)
+        out = src[np.clip(iy, 0, H - 1), np.clip(ix, 0, W - 1)]
+        return np.where(inb, out, fill).astype(src.dtype)
+
+    sx = _round_half_even_i64(mapx * F32(32))
+    sy = _round_half_even_i64(mapy * F32(32))
+    ix = _sat_short(sx >> 5)
+    iy = _sat_short(sy >> 5)
+    fxi = sx & 31
+    fyi = sy & 31
+    cv = fill.astype(wt)
+
+    if method == "linear":
+        fx = (fxi.astype(F32) * F32(1.0 / 32.0)).astype(F32)
+        fy = (fyi.astype(F32) * F32(1.0 / 32.0)).astype(F32)
+        wx = [F32(1) - fx, fx]
+        wy = [F32(1) - fy, fy]
+        acc = None
+        for k1 in range(2):
+            for k2 in range(2):
+                w = (wy[k1] * wx[k2]).astype(F32)
+                yy = iy + k1
+                xx = ix + k2
+                inb = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+                v = np.where(inb, src[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)], fill).astype(wt)
+                with np.errstate(invalid="ignore"):
+                    term = v * w.astype(wt)
+                    acc = term if acc is None else acc + term
+        outside = (ix >= W) | (ix + 1 < 0) | (iy >= H) | (iy + 1 < 0)
+        return np.where(outside, cv, acc).astype(src.dtype)
+
+    if method == "cubic":
+        cx = _cubic_coeffs(fxi)
+        cy = _cubic_coeffs(fyi)
+        x0 = ix - 1
+        y0 = iy - 1
+        fast = (x0 >= 0) & (x0 < max(W - 3, 0)) & (y0 >= 0) & (y0 < max(H - 3, 0))
+        outside = (x0 >= W) | (x0 + 4 <= 0) | (y0 >= H) | (y0 + 4 <= 0)
+        # fast path: sum over rows of (4-term row expression), left to right
+        acc_fast = None
+        # border path: cv + sum (S - cv) * w over in-bounds taps
+        with np.errstate(invalid="ignore"):
+            acc_b = cv * np.ones(mapx.shape, dtype=wt)
+            for k1 in range(4):
+                yy = y0 + k1
+                yin = (yy >= 0) & (yy < H)
+                row = None
+                for k2 in range(4):
+                    xx = x0 + k2
+                    xin = (xx >= 0) & (xx < W)
+                    w = (cy[..., k1] * cx[..., k2]).astype(F32).astype(wt)
+                    s = src[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)].astype(wt)
+                    t = s * w
+                    row = t if row is None else row + t
+                    acc_b = np.where(yin & xin, acc_b + (s - cv) * w, acc_b)
+                acc_fast = row if acc_fast is None else acc_fast + row
+        out = np.where(fast, acc_fast, acc_b)
+        return np.where(outside & ~fast, cv, out).astype(src.dtype)
+
+    raise NotImplementedError("lanczos interpolation is not restated in the oracle")
+
+
+def warp_positions(flow: np.ndarray, dx: int = 0, dy: int = 0):
+    """Sampling position p = fl32(fl32(flow + offset) + grid)   (convolve.py:56-63)."""
+    h, w = flow.shape[:2]
+    px = (flow[..., 0].astype(F32) + F32(dx)).astype(F32) + np.arange(w, dtype=F32)[None, :]
+    py = (flow[..., 1].astype(F32) + F32(dy)).astype(F32) + np.arange(h, dtype=F32)[:, None]
+    return px.astype(F32), py.astype(F32)

@@ -1,0 +1,157 @@
+"""Generate the committed golden vectors by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference and cv2):
+
+    python tests/golden/make_golden.py
+
+It imports ``/root/reference/tobac_flow`` under the dependency stubs of ``refshim.py`` and writes small
+``.npz`` fixtures next to this file.  Inputs are regenerated from seeds by
+``tobac_flow_b200.synthetic`` and are NOT stored.  The fixtures record the versions they came from.
+"""
+import hashlib
+import os
+import sys
+from functools import partial
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import refshim  # noqa: E402
+from tobac_flow_b200 import synthetic  # noqa: E402
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def small_bt():
+    """6 x 64 x 96 BT-like stack with NaN pixels, a NaN stripe and one all-NaN frame."""
+    bt = synthetic.bt_sequence(6, 64, 96, seed=42, nans=False)
+    rng = np.random.default_rng(7)
+    idx = rng.integers(0, bt.size, 40)
+    bt.reshape(-1)[idx] = np.nan
+    bt[2, 20:24] = np.nan
+    bt[4] = np.nan
+    return bt
+
+
+def three_level():
+    return synthetic.bt_sequence(3, 130, 170, seed=5, nans=False)
+
+
+def growth_case():
+    """12 x 120 x 160 wvd-like field with one fast-growing core (drives detect_growth_markers)."""
+    T, H, W = 12, 120, 160
+    base = synthetic.base_field(H, W, 99, sigma_px=10.0)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    wvd = np.empty((T, H, W), np.float32)
+    for t in range(T):
+        bg = -25.0 + 6.0 * np.roll(base, (t, 2 * t), (0, 1))
+        g = min(t, 8) / 8.0
+        cy, cx = 50 + t, 60 + 2 * t
+        core = (22.0 * g) * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * (5.0 + 5.0 * g) ** 2))
+        wvd[t] = bg + core
+    return wvd.astype(np.float32)
+
+
+def main():
+    import cv2
+    import scipy
+    import pandas as pd
+
+    refshim.load_reference()
+    from tobac_flow.flow import create_flow, Flow, smooth_flow_step
+    from tobac_flow import detection
+    from tobac_flow.utils import to_8bit, linear_norm
+    from scipy import ndimage as ndi
+
+    meta = dict(cv2=cv2.__version__, numpy=np.__version__, scipy=scipy.__version__)
+
+    # ---- G1: the survey's known-answer case -------------------------------------------------
+    data = synthetic.blob_stack()
+    f = create_flow(data)
+    d = f.diff(data)
+    s = f.sobel(data)
+    s_up_cubic = f.sobel(data, direction="uphill", method="cubic")
+    s_near = f.sobel(data, method="nearest")
+    c = f.convolve(data)
+    np.savez_compressed(
+        os.path.join(HERE, "blob100.npz"),
+        meta=str(meta),
+        fwd_0_4_9=f.forward_flow[[0, 4, 9]].astype(np.float32), bwd_4=f.backward_flow[4],
+        diff_4=d[4], sobel_4=s[4], sobel_up_cubic_4=s_up_cubic[4], sobel_near_4=s_near[4],
+        conv_nan_counts=np.isnan(c).sum((1, 2, 3)),
+        sha=np.array([sha16(f.forward_flow), sha16(f.backward_flow), sha16(d), sha16(s), sha16(c)]),
+    )
+
+    # ---- small BT stack with NaNs: every operator, reference flow stored ---------------------
+    bt = small_bt()
+    f = create_flow(bt)
+    q = np.stack([np.stack(to_8bit(linear_norm(bt[i:i + 2]), 0, 1)) for i in range(bt.shape[0] - 1)])
+    out = dict(meta=str(meta), q=q, fwd=f.forward_flow, bwd=f.backward_flow)
+    out["diff"] = f.diff(bt)
+    out["diff_nearest"] = f.diff(bt, method="nearest")
+    out["sobel"] = f.sobel(bt)
+    out["sobel_f32"] = f.sobel(bt, dtype=np.float32)
+    out["sobel_uphill_cubic"] = f.sobel(bt, direction="uphill", method="cubic")
+    out["sobel_downhill"] = f.sobel(bt, direction="downhill")
+    out["conv7_t13"] = f.convolve(bt)[:, [1, 3]]
+    out["conv7_cubic_fill0_t13"] = f.convolve(bt, method="cubic", fill_value=0.0)[:, [1, 3]]
+    t_struct = np.zeros([3, 3, 3])
+    t_struct[:, 1, 1] = 1
+    raw64 = out["diff"] / np.full(bt.shape[0], 5.0)[:, None, None]  # float64, as detection.py:99-101
+    out["tmean_f64src"] = f.convolve(raw64, structure=t_struct, func=lambda x: np.nanmean(x, 0))
+    s_struct = ndi.generate_binary_structure(3, 1)
+    s_struct[0] = 0
+    s_struct[2] = 0
+    out["smean"] = f.convolve(out["diff"], structure=s_struct, func=lambda x: np.nanmean(x, 0))
+    mask = (np.nan_to_num(bt, nan=300.0) < 250).astype(int)
+    out["any_nearest"] = f.convolve(mask, structure=t_struct.astype(bool), method="nearest",
+                                    fill_value=False, dtype=np.int32, func=partial(np.any, axis=0))
+    labels = ndi.label(mask)[0].astype(np.int32)
+    l_struct = ndi.generate_binary_structure(3, 1)
+    l_struct[1] = 0
+    out["labels_nearest"] = f.convolve(labels, structure=l_struct, method="nearest", dtype=np.int32,
+                                       fill_value=0)
+    # production flow settings minus variational refinement: one smoothing pass, cubic
+    fs = create_flow(bt, smoothing_passes=1, interp_method="cubic")
+    out["fwd_smooth1_cubic"] = fs.forward_flow
+    out["bwd_smooth1_cubic"] = fs.backward_flow
+    np.savez_compressed(os.path.join(HERE, "bt_small.npz"), **out)
+
+    # ---- three pyramid levels with half-even level sizes --------------------------------------
+    bt3 = three_level()
+    f3 = create_flow(bt3)
+    np.savez_compressed(os.path.join(HERE, "three_level.npz"), meta=str(meta),
+                        fwd_0=f3.forward_flow[0], bwd_1=f3.backward_flow[1])
+
+    # ---- downstream consumer: detect_growth_markers -------------------------------------------
+    wvd = growth_case()
+    t = pd.date_range("2020-01-01", periods=wvd.shape[0], freq="5min")
+    fg = create_flow(wvd)
+    # store the flow on a 1/256 px grid (int16 compresses well); the reference is then run on exactly
+    # the stored, de-quantised flow so both sides of the parity test see identical flow fields
+    fq = np.round(fg.forward_flow * 256).astype(np.int16)
+    bq = np.round(fg.backward_flow * 256).astype(np.int16)
+    fg = Flow(fq.astype(np.float32) / 256, bq.astype(np.float32) / 256)
+    da = refshim.DataArray(wvd, coords={"t": t}, dims=("t", "y", "x"), t=t)
+    # label.py warns when int32 would overflow; detection needs xr.DataArray isinstance to be our stub
+    smoothed, markers = detection.detect_growth_markers(fg, da)
+    markers = np.asarray(markers.data if hasattr(markers, "data") else markers)
+    s2 = ndi.generate_binary_structure(2, 1)[np.newaxis, ...]
+    filtered = ndi.grey_opening(smoothed, footprint=s2) * detection.get_curvature_filter(wvd)
+    np.savez_compressed(os.path.join(HERE, "growth.npz"), meta=str(meta),
+                        fwd_q256=fq, bwd_q256=bq,
+                        smoothed_even=smoothed[::2].astype(np.float32),
+                        mask025=np.packbits(filtered >= 0.25), mask05=np.packbits(filtered >= 0.5), markers=markers.astype(np.int32),
+                        n_markers=np.array(int(markers.max())))
+    print("growth markers:", int(markers.max()), "marked px:", int((markers > 0).sum()))
+    for n in ("blob100", "bt_small", "three_level", "growth"):
+        print(n, os.path.getsize(os.path.join(HERE, n + ".npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
