@@ -1,0 +1,148 @@
+/*
+ * tobac_flow_b200 — C ABI of the B200-native dense-flow hot path.
+ *
+ * This is the drop-in boundary: plain C, device pointers and sizes only (no torch types).  Each entry
+ * point names the reference code it replaces (paths relative to the tobac-flow repository).  The
+ * reference is Python on numpy + OpenCV, so a maintainer binds these with ctypes (INTEGRATION.md shows
+ * the stub); `tobac_flow_b200/_lib.py` is that binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless marked "host";
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous;
+ *   - images are row-major (H, W); frame stacks (T, H, W); flow fields (H, W, 2) interleaved float32 with
+ *     [...,0] = dx along W and [...,1] = dy along H   (tobac_flow/flow.py:408-416);
+ *   - functions return 0 on success or a negative tf_status; tf_last_error() returns a thread-local
+ *     human-readable message for the last failure.  Nothing throws, nothing falls back to the CPU.
+ */
+#ifndef TOBAC_FLOW_B200_H
+#define TOBAC_FLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TF_ABI_VERSION 1
+
+typedef enum tf_status {
+    TF_OK = 0,
+    TF_ERR_INVALID_ARGUMENT = -1,
+    TF_ERR_WORKSPACE_TOO_SMALL = -2,
+    TF_ERR_CUDA = -3,
+    TF_ERR_UNSUPPORTED = -4
+} tf_status;
+
+/* element types of stencil operands/results */
+typedef enum tf_dtype { TF_F32 = 0, TF_F64 = 1, TF_I32 = 2 } tf_dtype;
+
+/* cv2.remap interpolation modes used by tobac_flow/convolve.py:46-54 */
+typedef enum tf_interp { TF_NEAREST = 0, TF_LINEAR = 1, TF_CUBIC = 2 } tf_interp;
+
+/* per-step reducers (`func=`) the reference and its callers apply to the (n_taps, H, W) tap stack */
+typedef enum tf_reducer {
+    TF_RED_NONE = 0,           /* func=None: return the tap stack            convolve.py:332-345      */
+    TF_RED_DIFF = 1,           /* Flow.diff reducer                          flow.py:182-186          */
+    TF_RED_NANMEAN = 2,        /* lambda x: np.nanmean(x, 0)                 detection.py:53-55,187   */
+    TF_RED_ANY = 3,            /* partial(np.any, axis=0)                    detection.py:313-320     */
+    TF_RED_SOBEL = 4,          /* _sobel_func                                sobel.py:70-86           */
+    TF_RED_SOBEL_UPHILL = 5,   /* _sobel_func_uphill                         sobel.py:32-48           */
+    TF_RED_SOBEL_DOWNHILL = 6, /* _sobel_func_downhill                       sobel.py:51-67           */
+    TF_RED_NANMAX = 7,         /* lambda x: np.nanmax(x, 0)   (commented-out variant, detection.py:57) */
+    TF_RED_NANMIN = 8
+} tf_reducer;
+
+/* cv2.FarnebackOpticalFlow parameters; tf_fb_default_params() gives the factory defaults that
+ * tobac_flow/utils/flow_utils.py:52-53 (cv2.optflow.createOptFlow_Farneback()) uses. */
+typedef struct tf_fb_params {
+    int num_levels;    /* 5   */
+    double pyr_scale;  /* 0.5 (only 0.5 is supported) */
+    int win_size;      /* 13  (odd, <= 25) */
+    int num_iters;     /* 10  */
+    int poly_n;        /* 5   (only 5 is supported) */
+    double poly_sigma; /* 1.1 */
+    float max_value;   /* clamp applied to the final flow (flow.py:60-61); <= 0 disables */
+} tf_fb_params;
+
+int tf_version(void);
+const char* tf_last_error(void);
+void tf_fb_default_params(tf_fb_params* p /* host */);
+
+/* Number of pyramid levels OpenCV processes for an H x W image and, optionally, their sizes
+ * (coarsest first; `hs`/`ws` host arrays of >= 8 ints, may be NULL). */
+int tf_fb_level_plan(int H, int W, const tf_fb_params* p /* host */, int* hs /* host */, int* ws /* host */);
+
+/* Host-side diagnostic: the polynomial-expansion constants of OpenCV's FarnebackPrepareGaussian for
+ * (poly_n, poly_sigma): out[0..5] = g[0..5], out[6..11] = xg, out[12..17] = xxg, out[18..21] = ig11, ig03, ig33,
+ * ig55.  `out` is a host array of 22 floats. */
+int tf_fb_poly_constants(const tf_fb_params* p /* host */, float* out /* host */);
+
+/* Bytes of scratch tf_farneback_pairs needs for `n_pairs` pairs of H x W frames. */
+size_t tf_farneback_workspace_bytes(int n_pairs, int H, int W, const tf_fb_params* p /* host */);
+
+/*
+ * Per-pair normalisation + 8-bit quantisation.
+ * Replaces linear_norm (tobac_flow/utils/normalisation_utils.py:59-72) followed by to_8bit(., 0, 1)
+ * (:10-33) as called from calculate_flow (tobac_flow/flow.py:411-414): NaN-aware min/max over the
+ * two-frame stack, scale to [0, 1], x255, non-finite -> 127 then patched from the other frame, truncate.
+ * Pair p reads f0 + p*frame_stride and f1 + p*frame_stride (elements); writes q0/q1 + p*H*W.
+ * `minmax_scratch`: 2*n_pairs floats.
+ */
+int tf_pair_normalise_u8(const float* f0, const float* f1, long long frame_stride, uint8_t* q0, uint8_t* q1,
+                         int n_pairs, int H, int W, float* minmax_scratch, void* stream);
+
+/*
+ * Forward and backward Farneback flow for n_pairs quantised pairs.
+ * Replaces of_model.calc(prev, next, None) and of_model.calc(next, prev, None)
+ * (tobac_flow/flow.py:511,516; OpenCV FarnebackOpticalFlow::calc, flags = 0) including the clamp of
+ * create_flow (flow.py:60-61).  Pair p: images q0/q1 + p*H*W; results fwd + p*fwd_stride and
+ * bwd + p*bwd_stride (elements; calculate_flow stores them at forward_flow[i], backward_flow[i+1]).
+ */
+int tf_farneback_pairs(const uint8_t* q0, const uint8_t* q1, float* fwd, long long fwd_stride, float* bwd,
+                       long long bwd_stride, int n_pairs, int H, int W, const tf_fb_params* p /* host */,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * One smooth_flow_step (tobac_flow/flow.py:530-568) on n_pairs (fwd, bwd) fields in place semantics:
+ * fwd' = nanmean(fwd, -warp(bwd by fwd)), bwd' = nanmean(bwd, -warp(fwd by bwd)), both from the old
+ * fields; results go to fwd_out/bwd_out (must not alias the inputs).
+ */
+int tf_smooth_flow_step(const float* fwd, const float* bwd, float* fwd_out, float* bwd_out, long long stride,
+                        int n_pairs, int H, int W, int interp, void* stream);
+
+/*
+ * Sequence end rules + clamp: forward[T-1] = -backward[T-1] (if mirror_last), backward[0] = -forward[0]
+ * (if mirror_first)  (tobac_flow/flow.py:425-426), then clamp everything to +-max_value if max_value > 0
+ * and `clamp_all` (flow.py:60-61).  fwd/bwd: (T, H, W, 2).
+ */
+int tf_flow_finalise(float* fwd, float* bwd, int T, int H, int W, float max_value, int clamp_all,
+                     int mirror_first, int mirror_last, void* stream);
+
+/*
+ * Semi-Lagrangian 3x3x3 tap gather with a fused per-step reducer.
+ * Replaces convolve.convolve / convolve_step / warp_flow / convolve_same_step
+ * (tobac_flow/convolve.py:8-348), cv2.remap(BORDER_CONSTANT, fill) and the reducers listed in tf_reducer,
+ * i.e. Flow.convolve / Flow.diff / Flow.sobel (tobac_flow/flow.py:105-234, tobac_flow/sobel.py).
+ *
+ *   cur0        frame t0 of the operand; frames contiguous, H*W elements apart, element type src_dtype
+ *   n_frames    frames processed: t0 .. t0+n_frames-1
+ *   has_prev    non-zero if frame t0-1 exists in memory at cur0 - H*W (else it is an all-`fill` frame,
+ *               convolve.py:307-310);  has_next likewise for frame t0+n_frames (convolve.py:311-314)
+ *   fflow0/bflow0   forward/backward flow of frame t0, (n_frames, H, W, 2) float32
+ *   structure27 host array of 27 bytes, the 3x3x3 structuring element (non-zero = tap), order [t][y][x]
+ *   stack_dtype the `dtype=` argument (type of the tap stack and of the result)
+ *   out         reducer == TF_RED_NONE: (n_taps, n_frames, H, W) with tap stride `out_tap_stride` elements;
+ *               otherwise (n_frames, H, W)
+ *   fill        fill_value
+ * With a reducer, outputs where the operand is NaN are set to `fill` (convolve.py:346-347).
+ */
+int tf_sl_convolve(const void* cur0, int n_frames, int has_prev, int has_next, const float* fflow0,
+                   const float* bflow0, void* out, long long out_tap_stride, int H, int W, int src_dtype,
+                   int stack_dtype, int interp, int reducer, const uint8_t* structure27 /* host */,
+                   double fill, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOBAC_FLOW_B200_H */

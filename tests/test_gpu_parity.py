@@ -1,0 +1,297 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the reference's golden vectors.
+
+Tolerances (BASELINE.json north_star): flow mean end-point error <= 0.05 px and 99th percentile <= 0.5 px vs
+OpenCV Farneback; convolve / sobel / diff within 1e-4 relative with identical NaN masks when fed the reference's
+own flow fields (most are in fact bit-exact and asserted so); integer / byte results bit-exact.
+"""
+from functools import partial
+
+import numpy as np
+import pytest
+from scipy import ndimage as ndi
+
+pytestmark = pytest.mark.gpu
+
+from oracle import farneback_np, flow_ops as ops  # noqa: E402
+import make_golden as cases  # noqa: E402
+from tobac_flow_b200 import synthetic  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def tfb():
+    import tobac_flow_b200
+    return tobac_flow_b200
+
+
+def epe(a, b):
+    return np.sqrt(((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2).sum(-1))
+
+
+def assert_flow_close(mine, ref, mean_tol=0.05, p99_tol=0.5):
+    e = epe(mine, ref)
+    assert np.isfinite(e).all()
+    assert e.mean() <= mean_tol and np.percentile(e, 99) <= p99_tol, (e.mean(), np.percentile(e, 99), e.max())
+    return e
+
+
+def assert_close(a, b, rtol=1e-4):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN masks differ"
+    m = ~np.isnan(b)
+    err = np.abs(a[m] - b[m]) / np.maximum(np.abs(b[m]), 1.0)
+    assert err.size == 0 or err.max() <= rtol, err.max()
+
+
+def assert_same(a, b):
+    assert a.dtype == b.dtype and a.shape == b.shape
+    assert np.array_equal(a, b, equal_nan=True), f"max abs diff {np.nanmax(np.abs(a.astype(np.float64) - b))}"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# K1 normalisation / quantisation: bit-exact
+# ------------------------------------------------------------------------------------------------------------------
+def test_pair_quantisation_bit_exact(tfb, golden):
+    bt = cases.small_bt()
+    g = golden("bt_small")
+    for i in range(bt.shape[0] - 1):
+        q0, q1 = tfb.pair_to_8bit(bt[i], bt[i + 1])
+        assert np.array_equal(q0, g["q"][i, 0]) and np.array_equal(q1, g["q"][i, 1])
+    data = synthetic.blob_stack()
+    rng = np.random.default_rng(5)
+    odd = (rng.standard_normal((2, 37, 53)) * 1e3).astype(np.float32)  # odd size -> scalar path
+    odd[0, 3, 4] = np.inf
+    odd[1, 7, 7] = np.nan
+    const = np.full((2, 40, 40), 3.25, np.float32)                      # vmax == vmin -> factor 0
+    for a, b in ((data[0], data[1]), (odd[0], odd[1]), (const[0], const[1])):
+        q0, q1 = tfb.pair_to_8bit(a, b)
+        r0, r1 = ops.pair_to_u8(a, b)
+        assert np.array_equal(q0, r0) and np.array_equal(q1, r1)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Farneback flow vs the reference (cv2) goldens and the oracle
+# ------------------------------------------------------------------------------------------------------------------
+def test_flow_small_bt_vs_reference_golden(tfb, golden):
+    g = golden("bt_small")
+    f = tfb.create_flow(cases.small_bt())
+    e1 = assert_flow_close(f.forward_flow, g["fwd"], 1e-3, 1e-2)
+    e2 = assert_flow_close(f.backward_flow, g["bwd"], 1e-3, 1e-2)
+    print("bt_small EPE mean/max", e1.mean(), e1.max(), e2.mean(), e2.max())
+
+
+def test_flow_three_levels_vs_reference_golden(tfb, golden):
+    g = golden("three_level")
+    f = tfb.create_flow(cases.three_level())
+    assert_flow_close(f.forward_flow[0], g["fwd_0"], 1e-3, 1e-2)
+    assert_flow_close(f.backward_flow[1], g["bwd_1"], 1e-3, 1e-2)
+
+
+def test_flow_blob_known_answers(tfb, golden):
+    g = golden("blob100")
+    f = tfb.create_flow(synthetic.blob_stack())
+    assert_flow_close(f.forward_flow[[0, 4, 9]], g["fwd_0_4_9"], 1e-3, 1e-2)
+    assert_flow_close(f.backward_flow[4], g["bwd_4"], 1e-3, 1e-2)
+    assert np.allclose(f.forward_flow[4, 50, 50], (0.10432175, 0.10432258), atol=1e-4)
+    assert np.allclose(f.backward_flow[4, 50, 50], (-0.10804594, -0.10804673), atol=1e-4)
+    # end rules (flow.py:425-426)
+    assert np.array_equal(f.forward_flow[-1], -f.backward_flow[-1])
+    assert np.array_equal(f.backward_flow[0], -f.forward_flow[0])
+
+
+@pytest.mark.parametrize("shape", [(10, 15), (33, 47), (64, 64), (100, 259), (257, 130)])
+def test_flow_vs_oracle_odd_sizes(tfb, shape):
+    h, w = shape
+    bt = synthetic.bt_sequence(3, h, w, seed=h * 7 + w, nans=False)
+    f = tfb.create_flow(bt)
+    ref_f, ref_b = ops.create_flow(bt, backend="cv2" if ops.have_cv2() else "numpy")
+    assert_flow_close(f.forward_flow, ref_f, 2e-3, 2e-2)
+    assert_flow_close(f.backward_flow, ref_b, 2e-3, 2e-2)
+
+
+def test_identical_frames_give_zero_flow(tfb):
+    bt = synthetic.bt_sequence(1, 96, 128, seed=3, nans=False)
+    f = tfb.create_flow(np.repeat(bt, 3, 0))
+    assert np.abs(f.forward_flow).max() < 1e-4 and np.abs(f.backward_flow).max() < 1e-4
+
+
+def test_clamp_and_calculate_flow(tfb):
+    bt = synthetic.bt_sequence(3, 80, 120, seed=11, nans=False)
+    fwd, bwd = tfb.calculate_flow(bt)
+    f = tfb.create_flow(bt, max_value=0.25)
+    assert np.array_equal(f.forward_flow, np.clip(fwd, -0.25, 0.25))
+    assert np.array_equal(f.backward_flow, np.clip(bwd, -0.25, 0.25))
+
+
+def test_smoothing_passes_vs_reference_golden(tfb, golden):
+    g = golden("bt_small")
+    # smooth_flow_step itself, fed with the reference's un-smoothed fields
+    f, b = tfb.smooth_flow_step(g["fwd"][0], g["bwd"][1], method="cubic")
+    rf, rb = ops.smooth_flow_step(g["fwd"][0], g["bwd"][1], "cubic")
+    assert_same(f, rf.astype(np.float32))
+    assert_same(b, rb.astype(np.float32))
+    fl = tfb.create_flow(cases.small_bt(), smoothing_passes=1, interp_method="cubic")
+    assert_flow_close(fl.forward_flow, g["fwd_smooth1_cubic"], 1e-3, 1e-2)
+    assert_flow_close(fl.backward_flow, g["bwd_smooth1_cubic"], 1e-3, 1e-2)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# stencil operators fed with the REFERENCE's flow fields
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ref_flow(tfb, golden):
+    g = golden("bt_small")
+    return tfb.Flow(g["fwd"], g["bwd"]), cases.small_bt(), g
+
+
+def test_diff(ref_flow):
+    fl, bt, g = ref_flow
+    assert_same(fl.diff(bt), g["diff"])
+    assert_same(fl.diff(bt, method="nearest"), g["diff_nearest"])
+
+
+def test_sobel(ref_flow):
+    fl, bt, g = ref_flow
+    s = fl.sobel(bt)
+    assert s.dtype == np.float64
+    assert_close(s, g["sobel"], 1e-12)
+    assert_close(fl.sobel(bt, dtype=np.float32), g["sobel_f32"], 1e-6)
+    assert_close(fl.sobel(bt, direction="uphill", method="cubic"), g["sobel_uphill_cubic"], 1e-12)
+    assert_close(fl.sobel(bt, direction="downhill"), g["sobel_downhill"], 1e-12)
+
+
+def test_convolve_stack(ref_flow):
+    fl, bt, g = ref_flow
+    c = fl.convolve(bt)
+    assert c.shape == (7,) + bt.shape and c.dtype == np.float32
+    assert_same(c[:, [1, 3]], g["conv7_t13"])
+    assert_same(fl.convolve(bt, method="cubic", fill_value=0.0)[:, [1, 3]], g["conv7_cubic_fill0_t13"])
+
+
+def test_convolve_reducers(ref_flow):
+    fl, bt, g = ref_flow
+    t_struct = np.zeros([3, 3, 3])
+    t_struct[:, 1, 1] = 1
+    raw64 = g["diff"] / np.full(bt.shape[0], 5.0)[:, None, None]
+    assert raw64.dtype == np.float64
+    assert_same(fl.convolve(raw64, structure=t_struct, func=lambda x: np.nanmean(x, 0)), g["tmean_f64src"])
+    s_struct = ndi.generate_binary_structure(3, 1)
+    s_struct[0] = 0
+    s_struct[2] = 0
+    assert_same(fl.convolve(g["diff"], structure=s_struct, func=lambda x: np.nanmean(x, 0)), g["smean"])
+    mask = (np.nan_to_num(bt, nan=300.0) < 250).astype(int)
+    assert_same(fl.convolve(mask, structure=t_struct.astype(bool), method="nearest", fill_value=False,
+                            dtype=np.int32, func=partial(np.any, axis=0)), g["any_nearest"])
+    labels = ndi.label(mask)[0].astype(np.int32)
+    l_struct = ndi.generate_binary_structure(3, 1)
+    l_struct[1] = 0
+    assert_same(fl.convolve(labels, structure=l_struct, method="nearest", dtype=np.int32, fill_value=0),
+                g["labels_nearest"])
+
+
+def test_unrecognised_python_reducer_uses_stack_path(ref_flow):
+    fl, bt, g = ref_flow
+    func = lambda x: np.nanmedian(x, 0)  # noqa: E731
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = ops.convolve(bt, g["fwd"], g["bwd"], func=func)
+        got = fl.convolve(bt, func=func)
+    assert_same(got, want)
+
+
+def test_blob_stencil_known_answers(tfb, golden):
+    g1 = golden("blob100")
+    data = synthetic.blob_stack()
+    fwd = np.zeros(data.shape + (2,), np.float32)
+    bwd = np.zeros(data.shape + (2,), np.float32)
+    fwd[4] = g1["fwd_0_4_9"][1]
+    bwd[4] = g1["bwd_4"]
+    fl = tfb.Flow(fwd, bwd)
+    d = fl.diff(data)[4]
+    assert_same(d, g1["diff_4"])
+    assert d[50, 50] == -30920.5
+    s = fl.sobel(data)[4]
+    assert_close(s, g1["sobel_4"], 1e-12)
+    assert abs(s[50, 50] - 1254683.1562226177) < 1e-6
+    assert_close(fl.sobel(data, direction="uphill", method="cubic")[4], g1["sobel_up_cubic_4"], 1e-12)
+    assert_close(fl.sobel(data, method="nearest")[4], g1["sobel_near_4"], 1e-12)
+
+
+def test_reference_test_detection_edge_field(tfb):
+    """Restates the reference's only Flow.sobel test (tests/test_detection.py:36-60): zero flow, 1x5x5 step
+    field, uphill + cubic, NaN where the field is NaN."""
+    field = np.zeros((1, 5, 5), np.float32)
+    field[..., 3:] = 1
+    field[0, 0, 0] = np.nan
+    z = np.zeros((1, 5, 5, 2), np.float32)
+    fl = tfb.Flow(z, z)
+    got = fl.sobel(field, direction="uphill", method="cubic")
+    want = ops.sobel(field, z, z, "cubic", None, direction="uphill")
+    assert_close(got, want, 1e-12)
+    assert np.isnan(got[0, 0, 0])
+
+
+def test_function_level_mirrors(tfb, golden):
+    from tobac_flow_b200 import convolve as cmod, sobel as smod
+    g = golden("bt_small")
+    bt = cases.small_bt()
+    assert_same(cmod.convolve(bt, g["fwd"], g["bwd"])[:, [1, 3]], g["conv7_t13"])
+    assert_close(smod.sobel(bt, g["fwd"], g["bwd"]), g["sobel_f32"], 1e-6)
+    offs = np.array([[1, 0], [0, -1], [-1, 1]])
+    w = cmod.warp_flow(bt[1], g["fwd"][0], offsets=offs)
+    for k, (dx, dy) in enumerate(offs):
+        assert_same(w[k], ops.warp_image(bt[1], g["fwd"][0], "linear", np.nan, dx, dy))
+
+
+def test_error_conventions(tfb):
+    z = np.zeros((2, 8, 9, 2), np.float32)
+    with pytest.raises(ValueError):
+        tfb.Flow(z, z[:1])
+    with pytest.raises(ValueError):
+        tfb.Flow(z[..., :1], z[..., :1])
+    fl = tfb.Flow(z, z)
+    assert fl.shape == (2, 8, 9)
+    with pytest.raises(AssertionError):
+        fl.convolve(np.zeros((2, 8, 8), np.float32))
+    with pytest.raises(AssertionError):
+        fl.convolve(np.zeros((2, 8, 9), np.float32), structure=np.ones((3, 3)))
+    with pytest.raises(ValueError):
+        fl.convolve(np.zeros((2, 8, 9), np.float32), method="bogus")
+    with pytest.raises(ValueError):
+        tfb.create_flow(np.zeros((2, 40, 40), np.float32), model="bogus")
+    with pytest.raises(NotImplementedError):
+        tfb.create_flow(np.zeros((2, 40, 40), np.float32), model="DIS")
+    sub = fl[0:1]
+    assert sub.shape == (1, 8, 9)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# downstream: growth markers (detection.py:98-125) up to the thresholds that define the marker masks
+# ------------------------------------------------------------------------------------------------------------------
+def test_growth_marker_masks_bit_exact(tfb, golden):
+    g = golden("growth")
+    wvd = cases.growth_case()
+    fl = tfb.Flow(g["fwd_q256"].astype(np.float32) / 256, g["bwd_q256"].astype(np.float32) / 256)
+    dt = np.full(wvd.shape[0], 5.0)                                   # get_time_diff_from_coord of a 5-min axis
+    raw = fl.diff(wvd) / dt[:, None, None]                             # detection.py:99-101 (float64)
+    t_struct = np.zeros([3, 3, 3])
+    t_struct[:, 1, 1] = 1
+    smoothed = fl.convolve(raw, structure=t_struct, func=lambda x: np.nanmean(x, 0))   # detection.py:53-55
+    assert_same(smoothed[::2], g["smoothed_even"])
+    # detection.py:105-108 + get_curvature_filter :64-94 (scipy, downstream of the hot path)
+    s_struct = ndi.generate_binary_structure(2, 1)[np.newaxis, ...]
+    sm = ndi.gaussian_filter(wvd, (0, 2, 2))
+    x_diff = np.zeros(wvd.shape)
+    x_diff[:, :, 1:-1] = np.diff(sm, n=2, axis=2)
+    y_diff = np.zeros(wvd.shape)
+    y_diff[:, 1:-1] = np.diff(sm, n=2, axis=1)
+    s3 = ndi.generate_binary_structure(3, 1)
+    s3[0] = 0
+    s3[2] = 0
+    curv = ndi.binary_opening(ndi.binary_fill_holes(np.logical_and(x_diff < 0, y_diff < 0), structure=s3), structure=s3)
+    filtered = ndi.grey_opening(smoothed, footprint=s_struct) * curv
+    assert np.array_equal(np.packbits(filtered >= 0.25), g["mask025"])
+    assert np.array_equal(np.packbits(filtered >= 0.5), g["mask05"])
+    assert (filtered >= 0.5).sum() > 0

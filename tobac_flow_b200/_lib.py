@@ -1,0 +1,114 @@
+"""ctypes binding of the C-ABI library (include/tobac_flow_b200.h).
+
+This is the only place the package touches native code.  There is no CPU fallback: if the shared library is
+missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtobacflow_b200.so")
+
+TF_F32, TF_F64, TF_I32 = 0, 1, 2
+TF_NEAREST, TF_LINEAR, TF_CUBIC = 0, 1, 2
+(TF_RED_NONE, TF_RED_DIFF, TF_RED_NANMEAN, TF_RED_ANY, TF_RED_SOBEL, TF_RED_SOBEL_UPHILL,
+ TF_RED_SOBEL_DOWNHILL, TF_RED_NANMAX, TF_RED_NANMIN) = range(9)
+
+# every symbol include/tobac_flow_b200.h declares
+EXPORTS = (
+    "tf_version", "tf_last_error", "tf_fb_default_params", "tf_fb_level_plan", "tf_fb_poly_constants",
+    "tf_farneback_workspace_bytes", "tf_pair_normalise_u8", "tf_farneback_pairs", "tf_smooth_flow_step",
+    "tf_flow_finalise", "tf_sl_convolve",
+)
+
+
+class FbParams(ctypes.Structure):
+    _fields_ = [
+        ("num_levels", ctypes.c_int), ("pyr_scale", ctypes.c_double), ("win_size", ctypes.c_int),
+        ("num_iters", ctypes.c_int), ("poly_n", ctypes.c_int), ("poly_sigma", ctypes.c_double),
+        ("max_value", ctypes.c_float),
+    ]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libtobacflow_b200.so (built by ``python -m tobac_flow_b200.build``); raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            f"{LIB_PATH} not found: build it with `python -m tobac_flow_b200.build` "
+            "(tobac_flow_b200 has no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ll, ci, cf, cd = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float, ctypes.c_double
+    pp = ctypes.POINTER(FbParams)
+    lib.tf_version.restype = ci
+    lib.tf_last_error.restype = ctypes.c_char_p
+    lib.tf_fb_default_params.argtypes = [pp]
+    lib.tf_fb_default_params.restype = None
+    lib.tf_fb_level_plan.argtypes = [ci, ci, pp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.tf_fb_poly_constants.argtypes = [pp, ctypes.POINTER(cf)]
+    lib.tf_farneback_workspace_bytes.argtypes = [ci, ci, ci, pp]
+    lib.tf_farneback_workspace_bytes.restype = ctypes.c_size_t
+    lib.tf_pair_normalise_u8.argtypes = [vp, vp, ll, vp, vp, ci, ci, ci, vp, vp]
+    lib.tf_farneback_pairs.argtypes = [vp, vp, vp, ll, vp, ll, ci, ci, ci, pp, vp, ctypes.c_size_t, vp]
+    lib.tf_smooth_flow_step.argtypes = [vp, vp, vp, vp, ll, ci, ci, ci, ci, vp]
+    lib.tf_flow_finalise.argtypes = [vp, vp, ci, ci, ci, cf, ci, ci, ci, vp]
+    lib.tf_sl_convolve.argtypes = [vp, ci, ci, ci, vp, vp, vp, ll, ci, ci, ci, ci, ci, ci,
+                                   ctypes.POINTER(ctypes.c_uint8), cd, vp]
+    for name in ("tf_fb_level_plan", "tf_fb_poly_constants", "tf_pair_normalise_u8", "tf_farneback_pairs",
+                 "tf_smooth_flow_step", "tf_flow_finalise", "tf_sl_convolve"):
+        getattr(lib, name).restype = ci
+    if lib.tf_version() != 1:
+        raise NativeError("libtobacflow_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().tf_last_error().decode("utf-8", "replace")
+        raise NativeError(f"{what} failed with status {rc}: {msg}")
+
+
+def default_params(max_value=20.0):
+    p = FbParams()
+    load().tf_fb_default_params(ctypes.byref(p))
+    p.max_value = float(max_value) if max_value is not None else 0.0
+    return p
+
+
+def level_plan(H, W, params=None):
+    params = params or default_params()
+    hs = (ctypes.c_int * 8)()
+    ws = (ctypes.c_int * 8)()
+    n = load().tf_fb_level_plan(H, W, ctypes.byref(params), hs, ws)
+    if n < 0:
+        check(n, "tf_fb_level_plan")
+    return [(hs[i], ws[i]) for i in range(n)]
+
+
+def poly_constants(params=None):
+    params = params or default_params()
+    out = (ctypes.c_float * 22)()
+    check(load().tf_fb_poly_constants(ctypes.byref(params), out), "tf_fb_poly_constants")
+    return np.array(out, dtype=np.float32)
+
+
+def workspace_bytes(n_pairs, H, W, params=None):
+    params = params or default_params()
+    return int(load().tf_farneback_workspace_bytes(n_pairs, H, W, ctypes.byref(params)))
+
+
+def structure_bytes(structure):
+    s = np.ascontiguousarray(np.asarray(structure) != 0, dtype=np.uint8).reshape(27)
+    return (ctypes.c_uint8 * 27)(*s.tolist())

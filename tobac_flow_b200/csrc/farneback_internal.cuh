@@ -1,0 +1,38 @@
+// Internal launch interfaces shared by the Farneback translation units.
+#pragma once
+#include "tf_common.cuh"
+
+namespace tf {
+
+constexpr int kMaxBlurTaps = 96;
+struct BlurTaps {
+    int ksize;
+    float w[kMaxBlurTaps];
+};
+
+struct PolyConsts {
+    float g[6], xg[6], xxg[6];  // g[k], k = 0..5 (symmetric / antisymmetric about 0)
+    float ig11, ig03, ig33, ig55;
+};
+PolyConsts make_poly_consts(int n, double sigma);
+
+// level image for 2*n_pairs images: out (2*n_pairs, h, w); tmp >= 2*n_pairs * rows*W floats
+int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int H, int W, int h, int w, int ksize,
+                         double sigma, float* tmp, float* out, cudaStream_t s);
+
+// dst (n_fields, h, w, 2) = resize(src (n_fields, sh, sw, 2)) * mul; src == nullptr -> zeros
+int launch_flow_upsample(const float* src, float* dst, int n_fields, int sh, int sw, int h, int w, float mul,
+                         cudaStream_t s);
+
+// R (n_img, 5, h, w) planes from I (n_img, h, w)
+int launch_polyexp(const float* I, float* R, int n_img, int h, int w, const PolyConsts& pc, cudaStream_t s);
+
+// One Jacobi iteration (UpdateMatrices + 13x13 box + 2x2 solve) for n_pairs x 2 directions.
+//   R          (2*n_pairs, 5, h, w): image 2p = prev, 2p+1 = next
+//   flow_in    (n_pairs, 2, h, w, 2)   [pair][direction]
+//   out_fwd/out_bwd + p*stride: where direction 0 / 1 results go (h, w, 2)
+//   clamp > 0: clamp results to +-clamp
+int launch_fb_iteration(const float* R, const float* flow_in, float* out_fwd, long long fwd_stride, float* out_bwd,
+                        long long bwd_stride, int n_pairs, int h, int w, int win, float clamp, cudaStream_t s);
+
+}  // namespace tf

@@ -1,0 +1,469 @@
+// K8: semi-Lagrangian 3x3x3 tap gather with fused per-step reducers; K9: smooth_flow_step; K7: finalise.
+//
+// Replaces tobac_flow/convolve.py (warp_flow -> cv2.remap with BORDER_CONSTANT, convolve_same_step, convolve_step,
+// convolve) and the reducers of Flow.diff (flow.py:182-186), sobel.py and detection.py.  cv2.remap semantics are
+// reproduced exactly (see oracle/remap_np.py): 1/32-px coordinate quantisation with round-half-even, fp32 table
+// weights wy*wx, left-to-right accumulation without FMA contraction, per-tap constant border (NaN poisoning through
+// zero weights), short saturation of integer coordinates.
+//
+// One thread per output pixel; the tap stack lives in registers only.  HBM traffic per pixel-step: 3 operand frames
+// (neighbour re-reads hit L1/L2), 2 flow fields (16 B) and the result.
+#include "tf_common.cuh"
+
+namespace tf {
+
+enum RedClass { RC_NONE = 0, RC_DIFF = 1, RC_STAT = 2, RC_SOBEL = 3 };
+
+struct GatherArgs {
+    const void* cur0;
+    const float2* fflow0;
+    const float2* bflow0;
+    void* out;
+    long long out_tap_stride;
+    int n_frames, has_prev, has_next;
+    int H, W;
+    unsigned structure;  // bit k = tap k present, k = t*9 + y*3 + x
+    int reducer;         // tf_reducer
+    double fill;
+};
+
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+
+// cvRound on a float coordinate with x86 semantics for NaN/overflow (-> INT_MIN), then saturate_cast<short>
+__device__ __forceinline__ int cv_round_dev(float v) {
+    if (!(fabsf(v) < 2.0e9f)) return INT_MIN;
+    return __float2int_rn(v);
+}
+__device__ __forceinline__ int sat_short(int v) { return min(max(v, -32768), 32767); }
+
+// a source image that may be a real frame or the virtual all-`fill` frame of convolve.py:307-314
+template <typename T>
+struct FrameSrc {
+    const T* p;   // nullptr -> constant frame
+    T fill;
+    int H, W;
+    __device__ __forceinline__ T at(int y, int x) const { return p ? p[(long long)y * W + x] : fill; }
+};
+
+// strided view (component c of an interleaved (H, W, 2) flow field) for smooth_flow_step
+struct FlowCompSrc {
+    const float* p;
+    float fill;
+    int H, W;
+    __device__ __forceinline__ float at(int y, int x) const { return p[((long long)y * W + x) * 2]; }
+};
+
+__device__ __forceinline__ void cubic_coeffs(int fi, float c[4]) {
+    // interpolateCubic, A = -0.75, fp32, no contraction
+    const float A = -0.75f;
+    const float x = __fmul_rn((float)fi, 1.0f / 32.0f);
+    const float xp1 = __fadd_rn(x, 1.f);
+    c[0] = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, xp1), __fmul_rn(5.f, A)), xp1), __fmul_rn(8.f, A)), xp1),
+                     __fmul_rn(4.f, A));
+    c[1] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(A, 2.f), x), __fadd_rn(A, 3.f)), x), x), 1.f);
+    const float omx = __fsub_rn(1.f, x);
+    c[2] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(A, 2.f), omx), __fadd_rn(A, 3.f)), omx), omx), 1.f);
+    c[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.f, c[0]), c[1]), c[2]);
+}
+
+// cv2.remap at one position.  T: element type, Src: accessor with at(y, x), H, W, fill
+template <int INTERP, typename T, typename Src>
+__device__ __forceinline__ T remap_at(const Src& s, float px, float py) {
+    const int H = s.H, W = s.W;
+    if constexpr (INTERP == TF_NEAREST) {
+        const int ix = sat_short(cv_round_dev(px)), iy = sat_short(cv_round_dev(py));
+        if ((unsigned)ix < (unsigned)W && (unsigned)iy < (unsigned)H) return s.at(iy, ix);
+        return s.fill;
+    } else {
+        const int sx = cv_round_dev(__fmul_rn(px, 32.f)), sy = cv_round_dev(__fmul_rn(py, 32.f));
+        const int ix = sat_short(sx >> 5), iy = sat_short(sy >> 5);
+        const int fxi = sx & 31, fyi = sy & 31;
+        if constexpr (INTERP == TF_LINEAR) {
+            const float fx = (float)fxi * (1.0f / 32.0f), fy = (float)fyi * (1.0f / 32.0f);
+            const float wx0 = 1.f - fx, wy0 = 1.f - fy;  // exact
+            const T w00 = (T)(wy0 * wx0), w01 = (T)(wy0 * fx), w10 = (T)(fy * wx0), w11 = (T)(fy * fx);  // exact
+            T v00, v01, v10, v11;
+            if ((unsigned)ix < (unsigned)max(W - 1, 0) && (unsigned)iy < (unsigned)max(H - 1, 0)) {
+                v00 = s.at(iy, ix); v01 = s.at(iy, ix + 1); v10 = s.at(iy + 1, ix); v11 = s.at(iy + 1, ix + 1);
+            } else {
+                if (ix >= W || ix + 1 < 0 || iy >= H || iy + 1 < 0) return s.fill;
+                const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
+                const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
+                v00 = (y0 && x0) ? s.at(iy, ix) : s.fill;
+                v01 = (y0 && x1) ? s.at(iy, ix + 1) : s.fill;
+                v10 = (y1 && x0) ? s.at(iy + 1, ix) : s.fill;
+                v11 = (y1 && x1) ? s.at(iy + 1, ix + 1) : s.fill;
+            }
+            return add_rn(add_rn(add_rn(mul_rn(v00, w00), mul_rn(v01, w01)), mul_rn(v10, w10)), mul_rn(v11, w11));
+        } else {  // cubic
+            float cx[4], cy[4];
+            cubic_coeffs(fxi, cx);
+            cubic_coeffs(fyi, cy);
+            const int x0 = ix - 1, y0 = iy - 1;
+            if ((unsigned)x0 < (unsigned)max(W - 3, 0) && (unsigned)y0 < (unsigned)max(H - 3, 0)) {
+                T sum = (T)0;
+#pragma unroll
+                for (int k1 = 0; k1 < 4; ++k1) {
+                    T row = mul_rn(s.at(y0 + k1, x0), (T)__fmul_rn(cy[k1], cx[0]));
+#pragma unroll
+                    for (int k2 = 1; k2 < 4; ++k2)
+                        row = add_rn(row, mul_rn(s.at(y0 + k1, x0 + k2), (T)__fmul_rn(cy[k1], cx[k2])));
+                    sum = k1 == 0 ? row : add_rn(sum, row);
+                }
+                return sum;
+            }
+            if (x0 >= W || x0 + 4 <= 0 || y0 >= H || y0 + 4 <= 0) return s.fill;
+            const T cv = s.fill;
+            T sum = cv;  // cv * ONE
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1) {
+                const int yy = y0 + k1;
+                if ((unsigned)yy >= (unsigned)H) continue;
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) {
+                    const int xx = x0 + k2;
+                    if ((unsigned)xx < (unsigned)W)
+                        sum = add_rn(sum, mul_rn(sub_rn(s.at(yy, xx), cv), (T)__fmul_rn(cy[k1], cx[k2])));
+                }
+            }
+            return sum;
+        }
+    }
+}
+
+template <typename T> __device__ __forceinline__ bool is_nan(T v) { return v != v; }
+template <> __device__ __forceinline__ bool is_nan<int>(int) { return false; }
+template <typename T> __device__ __forceinline__ bool is_fin(T v) { return isfinite(v); }
+template <> __device__ __forceinline__ bool is_fin<int>(int) { return true; }
+
+template <typename S, typename D> __device__ __forceinline__ D cast_to(S v) { return (D)v; }
+
+template <typename T> __device__ __forceinline__ T nan_of() { return (T)NAN; }
+template <> __device__ __forceinline__ int nan_of<int>() { return 0; }
+
+template <typename T> __device__ __forceinline__ T fill_cast(double f) { return (T)f; }
+template <> __device__ __forceinline__ int fill_cast<int>(double f) {
+    if (!(f == f)) return 0;
+    return (int)f;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// reducers: fed taps in stack order (t-1 slab, t slab, t+1 slab; row-major inside), value already in stack dtype
+// ------------------------------------------------------------------------------------------------------------------
+template <typename ST>
+struct RedNone {
+    ST* out; long long tap_stride; long long pix;
+    __device__ __forceinline__ void add(int n, int, ST v) { out[n * tap_stride + pix] = v; }
+};
+
+template <typename ST>
+struct RedDiff {
+    ST x[3];
+    __device__ __forceinline__ void add(int n, int, ST v) { if (n < 3) x[n] = v; }
+    __device__ __forceinline__ ST finish() const {
+        const ST a = x[2] - x[1], b = x[1] - x[0];
+        const ST s = (is_nan(a) ? (ST)0 : a) + (is_nan(b) ? (ST)0 : b);
+        int cnt = (is_fin(x[2]) ? 1 : 0) + (is_fin(x[0]) ? 1 : 0);
+        cnt = max(cnt, 1);
+        return (ST)((double)s / (double)cnt);
+    }
+};
+
+template <typename ST>
+struct RedStat {  // nanmean / nanmax / nanmin / any
+    int mode; ST acc; int cnt; bool any;
+    __device__ __forceinline__ void init(int m) { mode = m; acc = (ST)0; cnt = 0; any = false; }
+    __device__ __forceinline__ void add(int, int, ST v) {
+        if (v != (ST)0) any = true;  // NaN != 0 is true, like np.any on floats
+        if (is_nan(v)) return;
+        if (mode == TF_RED_NANMEAN) acc = acc + v;
+        else if (mode == TF_RED_NANMAX) acc = cnt ? (v > acc ? v : acc) : v;
+        else if (mode == TF_RED_NANMIN) acc = cnt ? (v < acc ? v : acc) : v;
+        ++cnt;
+    }
+    __device__ __forceinline__ ST finish() const {
+        if (mode == TF_RED_ANY) return any ? (ST)1 : (ST)0;
+        if (mode == TF_RED_NANMEAN) return (ST)((double)acc / (double)cnt);  // 0/0 -> NaN like numpy
+        return cnt ? acc : nan_of<ST>();
+    }
+};
+
+template <typename ST>
+struct RedSobel {
+    int dir; ST centre; double gx, gy, gt;
+    __device__ __forceinline__ void init(int d, ST c) { dir = d; centre = c; gx = gy = gt = 0.0; }
+    __device__ __forceinline__ void add(int, int k, ST v) {
+        ST d = v - centre;
+        if (dir == TF_RED_SOBEL_UPHILL) d = is_nan(d) ? (ST)0 : (d > (ST)0 ? d : (ST)0);        // np.fmax(d, 0)
+        else if (dir == TF_RED_SOBEL_DOWNHILL) d = is_nan(d) ? (ST)0 : (d < (ST)0 ? d : (ST)0); // np.fmin(d, 0)
+        if (is_nan(d)) return;
+        const int t = k / 9, y = (k / 3) % 3, x = k % 3;
+        const int wt = 2 - (t - 1) * (t - 1), wy = 2 - (y - 1) * (y - 1), wx = 2 - (x - 1) * (x - 1);  // (1, 2, 1)
+        const double dd = (double)d;
+        gx += dd * (double)(wt * wy * (x - 1));
+        gy += dd * (double)(wx * wt * (y - 1));
+        gt += dd * (double)(wy * wx * (t - 1));
+    }
+    __device__ __forceinline__ ST finish() const { return (ST)sqrt(gx * gx + gy * gy + gt * gt); }
+};
+
+template <typename SrcT, typename ST, int INTERP, int RC>
+__global__ void __launch_bounds__(256) sl_gather_kernel(GatherArgs a) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int t = blockIdx.z;
+    if (x >= a.W || y >= a.H) return;
+    const int H = a.H, W = a.W;
+    const long long hw = (long long)H * W;
+    const long long pix = (long long)y * W + x;
+    const SrcT* cur = reinterpret_cast<const SrcT*>(a.cur0) + (long long)t * hw;
+    const SrcT fill_s = fill_cast<SrcT>(a.fill);
+    const ST fill_st = fill_cast<ST>(a.fill);
+    FrameSrc<SrcT> prev{(t > 0 || a.has_prev) ? cur - hw : nullptr, fill_s, H, W};
+    FrameSrc<SrcT> next{(t < a.n_frames - 1 || a.has_next) ? cur + hw : nullptr, fill_s, H, W};
+    const float2 bf = a.bflow0[(long long)t * hw + pix];
+    const float2 ff = a.fflow0[(long long)t * hw + pix];
+    const SrcT centre_src = cur[pix];
+
+    RedNone<ST> rn{reinterpret_cast<ST*>(a.out) + (long long)t * hw, a.out_tap_stride, pix};
+    RedDiff<ST> rd;
+    RedStat<ST> rs;
+    RedSobel<ST> rsob;
+    if (RC == RC_DIFF) { rd.x[0] = rd.x[1] = rd.x[2] = (ST)0; }
+    if (RC == RC_STAT) rs.init(a.reducer);
+    if (RC == RC_SOBEL) rsob.init(a.reducer, cast_to<SrcT, ST>(centre_src));
+
+    int n = 0;
+#pragma unroll 1
+    for (int slab = 0; slab < 3; ++slab) {
+        const unsigned bits = (a.structure >> (9 * slab)) & 0x1ffu;
+        if (!bits) continue;
+#pragma unroll 1
+        for (int j = 0; j < 9; ++j) {
+            if (!((bits >> j) & 1u)) continue;
+            const int dy = j / 3 - 1, dx = j % 3 - 1;
+            ST v;
+            if (slab == 1) {
+                const int yy = y + dy, xx = x + dx;
+                v = ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) ? cast_to<SrcT, ST>(cur[(long long)yy * W + xx])
+                                                                                 : fill_st;
+            } else {
+                const float2 f = slab == 0 ? bf : ff;
+                // p = fl32(fl32(flow + offset) + grid)   (convolve.py:56-63)
+                const float px = __fadd_rn(__fadd_rn(f.x, (float)dx), (float)x);
+                const float py = __fadd_rn(__fadd_rn(f.y, (float)dy), (float)y);
+                const SrcT sv = slab == 0 ? remap_at<INTERP, SrcT>(prev, px, py) : remap_at<INTERP, SrcT>(next, px, py);
+                v = cast_to<SrcT, ST>(sv);
+            }
+            const int k = slab * 9 + j;
+            if (RC == RC_NONE) rn.add(n, k, v);
+            if (RC == RC_DIFF) rd.add(n, k, v);
+            if (RC == RC_STAT) rs.add(n, k, v);
+            if (RC == RC_SOBEL) rsob.add(n, k, v);
+            ++n;
+        }
+    }
+    if (RC != RC_NONE) {
+        ST r;
+        if (RC == RC_DIFF) r = rd.finish();
+        if (RC == RC_STAT) r = rs.finish();
+        if (RC == RC_SOBEL) r = rsob.finish();
+        if (is_nan(centre_src)) r = fill_st;  // res[np.isnan(data)] = fill_value   (convolve.py:346-347)
+        reinterpret_cast<ST*>(a.out)[(long long)t * hw + pix] = r;
+    }
+}
+
+template <typename SrcT, typename ST, int INTERP, int RC>
+static int launch_gather(const GatherArgs& a, cudaStream_t s) {
+    dim3 block(32, 8);
+    for (int t0 = 0; t0 < a.n_frames; t0 += 65535) {
+        GatherArgs b = a;
+        const int nt = min(a.n_frames - t0, 65535);
+        const long long hw = (long long)a.H * a.W;
+        b.cur0 = reinterpret_cast<const SrcT*>(a.cur0) + t0 * hw;
+        b.fflow0 = a.fflow0 + t0 * hw;
+        b.bflow0 = a.bflow0 + t0 * hw;
+        b.out = reinterpret_cast<ST*>(a.out) + t0 * hw;
+        b.n_frames = nt;
+        b.has_prev = (t0 > 0) ? 1 : a.has_prev;
+        b.has_next = (t0 + nt < a.n_frames) ? 1 : a.has_next;
+        dim3 grid(cdiv(a.W, 32), cdiv(a.H, 8), nt);
+        sl_gather_kernel<SrcT, ST, INTERP, RC><<<grid, block, 0, s>>>(b);
+    }
+    return check_launch("tf_sl_convolve");
+}
+
+template <typename SrcT, typename ST, int INTERP>
+static int dispatch_rc(const GatherArgs& a, int rc, cudaStream_t s) {
+    switch (rc) {
+        case RC_NONE: return launch_gather<SrcT, ST, INTERP, RC_NONE>(a, s);
+        case RC_DIFF: return launch_gather<SrcT, ST, INTERP, RC_DIFF>(a, s);
+        case RC_STAT: return launch_gather<SrcT, ST, INTERP, RC_STAT>(a, s);
+        default: return launch_gather<SrcT, ST, INTERP, RC_SOBEL>(a, s);
+    }
+}
+
+template <typename SrcT, typename ST>
+static int dispatch_interp(const GatherArgs& a, int interp, int rc, cudaStream_t s) {
+    switch (interp) {
+        case TF_NEAREST: return dispatch_rc<SrcT, ST, TF_NEAREST>(a, rc, s);
+        case TF_LINEAR: return dispatch_rc<SrcT, ST, TF_LINEAR>(a, rc, s);
+        default: return dispatch_rc<SrcT, ST, TF_CUBIC>(a, rc, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K9 smooth_flow_step (flow.py:530-568):  a' = nanmean([a, -warp(b, by = a)])
+// ------------------------------------------------------------------------------------------------------------------
+template <int INTERP>
+__global__ void __launch_bounds__(256) smooth_flow_kernel(const float* __restrict__ fwd, const float* __restrict__ bwd,
+                                                          float* __restrict__ fwd_out, float* __restrict__ bwd_out,
+                                                          long long stride, int H, int W) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int p = blockIdx.z >> 1, which = blockIdx.z & 1;
+    const float* A = (which ? bwd : fwd) + p * stride;   // field being smoothed
+    const float* B = (which ? fwd : bwd) + p * stride;   // opposite field, warped by A
+    float* O = (which ? bwd_out : fwd_out) + p * stride;
+    const long long pix = (long long)y * W + x;
+    const float ax = A[2 * pix], ay = A[2 * pix + 1];
+    const float px = __fadd_rn(ax, (float)x), py = __fadd_rn(ay, (float)y);
+    float o[2] = {ax, ay};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        FlowCompSrc src{B + c, NAN, H, W};
+        const float wv = -remap_at<INTERP, float>(src, px, py);
+        // np.nanmean([a, w], 0): NaN -> 0, fp32 sum, divide by the count through fp64
+        const float a0 = o[c];
+        float sum = (a0 != a0 ? 0.f : a0) + (wv != wv ? 0.f : wv);
+        const int cnt = (a0 == a0) + (wv == wv);
+        o[c] = (float)((double)sum / (double)cnt);
+    }
+    O[2 * pix] = o[0];
+    O[2 * pix + 1] = o[1];
+}
+
+// K7: end rules + clamp (flow.py:425-426, 60-61)
+__global__ void __launch_bounds__(256) flow_finalise_kernel(float* __restrict__ fwd, float* __restrict__ bwd, int T,
+                                                            long long frame_elems, float max_value, int clamp_all,
+                                                            int mirror_first, int mirror_last) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (i >= frame_elems) return;
+    const long long o = (long long)t * frame_elems + i;
+    float f = fwd[o], b = bwd[o];
+    if (mirror_last && t == T - 1) f = -b;
+    if (mirror_first && t == 0) b = -f;
+    if (clamp_all && max_value > 0.f) {
+        // np.minimum(np.maximum(v, -m), m) propagates NaN
+        if (f == f) f = fminf(fmaxf(f, -max_value), max_value);
+        if (b == b) b = fminf(fmaxf(b, -max_value), max_value);
+    }
+    fwd[o] = f;
+    bwd[o] = b;
+}
+
+}  // namespace tf
+
+using namespace tf;
+
+extern "C" int tf_sl_convolve(const void* cur0, int n_frames, int has_prev, int has_next, const float* fflow0,
+                              const float* bflow0, void* out, long long out_tap_stride, int H, int W, int src_dtype,
+                              int stack_dtype, int interp, int reducer, const uint8_t* structure27, double fill,
+                              void* stream) {
+    if (n_frames == 0) return TF_OK;
+    if (!cur0 || !fflow0 || !bflow0 || !out || !structure27 || n_frames < 0 || H <= 0 || W <= 0) {
+        set_error("tf_sl_convolve: invalid argument");
+        return TF_ERR_INVALID_ARGUMENT;
+    }
+    if (interp < TF_NEAREST || interp > TF_CUBIC) { set_error("tf_sl_convolve: unknown interpolation %d", interp); return TF_ERR_INVALID_ARGUMENT; }
+    if (reducer < TF_RED_NONE || reducer > TF_RED_NANMIN) { set_error("tf_sl_convolve: unknown reducer %d", reducer); return TF_ERR_INVALID_ARGUMENT; }
+    GatherArgs a{};
+    a.cur0 = cur0; a.fflow0 = reinterpret_cast<const float2*>(fflow0); a.bflow0 = reinterpret_cast<const float2*>(bflow0);
+    a.out = out; a.out_tap_stride = out_tap_stride; a.n_frames = n_frames; a.has_prev = has_prev; a.has_next = has_next;
+    a.H = H; a.W = W; a.reducer = reducer; a.fill = fill;
+    int n_taps = 0;
+    for (int k = 0; k < 27; ++k) if (structure27[k]) { a.structure |= 1u << k; ++n_taps; }
+    int rc;
+    switch (reducer) {
+        case TF_RED_NONE: rc = RC_NONE; break;
+        case TF_RED_DIFF: rc = RC_DIFF; break;
+        case TF_RED_SOBEL: case TF_RED_SOBEL_UPHILL: case TF_RED_SOBEL_DOWNHILL: rc = RC_SOBEL; break;
+        default: rc = RC_STAT;
+    }
+    if (rc == RC_DIFF && n_taps != 3) { set_error("tf_sl_convolve: the diff reducer needs exactly 3 taps"); return TF_ERR_INVALID_ARGUMENT; }
+    if (rc == RC_SOBEL && n_taps != 27) { set_error("tf_sl_convolve: the sobel reducers need the full 27-tap structure"); return TF_ERR_INVALID_ARGUMENT; }
+    if (n_taps == 0) { set_error("tf_sl_convolve: empty structure"); return TF_ERR_INVALID_ARGUMENT; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (src_dtype == TF_I32) {
+        if (interp != TF_NEAREST) { set_error("tf_sl_convolve: integer operands support nearest interpolation only (as cv2.remap)"); return TF_ERR_UNSUPPORTED; }
+        if (stack_dtype != TF_I32) { set_error("tf_sl_convolve: integer operands need an int32 result dtype"); return TF_ERR_UNSUPPORTED; }
+        if (rc == RC_NONE) return launch_gather<int, int, TF_NEAREST, RC_NONE>(a, s);
+        if (rc == RC_STAT && (reducer == TF_RED_ANY || reducer == TF_RED_NANMAX || reducer == TF_RED_NANMIN))
+            return launch_gather<int, int, TF_NEAREST, RC_STAT>(a, s);
+        set_error("tf_sl_convolve: reducer %d is not available for int32 operands", reducer);
+        return TF_ERR_UNSUPPORTED;
+    }
+    if (src_dtype == TF_F32 && stack_dtype == TF_F32) return dispatch_interp<float, float>(a, interp, rc, s);
+    if (src_dtype == TF_F32 && stack_dtype == TF_F64) return dispatch_interp<float, double>(a, interp, rc, s);
+    if (src_dtype == TF_F64 && stack_dtype == TF_F32) return dispatch_interp<double, float>(a, interp, rc, s);
+    if (src_dtype == TF_F64 && stack_dtype == TF_F64) return dispatch_interp<double, double>(a, interp, rc, s);
+    set_error("tf_sl_convolve: unsupported dtype combination src=%d stack=%d", src_dtype, stack_dtype);
+    return TF_ERR_UNSUPPORTED;
+}
+
+extern "C" int tf_smooth_flow_step(const float* fwd, const float* bwd, float* fwd_out, float* bwd_out, long long stride,
+                                   int n_pairs, int H, int W, int interp, void* stream) {
+    if (n_pairs == 0) return TF_OK;
+    if (!fwd || !bwd || !fwd_out || !bwd_out || n_pairs < 0 || H <= 0 || W <= 0) {
+        set_error("tf_smooth_flow_step: invalid argument");
+        return TF_ERR_INVALID_ARGUMENT;
+    }
+    if (fwd == fwd_out || bwd == bwd_out) { set_error("tf_smooth_flow_step: outputs must not alias inputs"); return TF_ERR_INVALID_ARGUMENT; }
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 block(32, 8);
+    for (int p0 = 0; p0 < n_pairs; p0 += 32767) {
+        const int np = min(n_pairs - p0, 32767);
+        dim3 grid(cdiv(W, 32), cdiv(H, 8), 2 * np);
+        const float* f = fwd + p0 * stride; const float* b = bwd + p0 * stride;
+        float* fo = fwd_out + p0 * stride; float* bo = bwd_out + p0 * stride;
+        switch (interp) {
+            case TF_NEAREST: smooth_flow_kernel<TF_NEAREST><<<grid, block, 0, s>>>(f, b, fo, bo, stride, H, W); break;
+            case TF_LINEAR: smooth_flow_kernel<TF_LINEAR><<<grid, block, 0, s>>>(f, b, fo, bo, stride, H, W); break;
+            case TF_CUBIC: smooth_flow_kernel<TF_CUBIC><<<grid, block, 0, s>>>(f, b, fo, bo, stride, H, W); break;
+            default: set_error("tf_smooth_flow_step: unknown interpolation %d", interp); return TF_ERR_INVALID_ARGUMENT;
+        }
+    }
+    return check_launch("tf_smooth_flow_step");
+}
+
+extern "C" int tf_flow_finalise(float* fwd, float* bwd, int T, int H, int W, float max_value, int clamp_all,
+                                int mirror_first, int mirror_last, void* stream) {
+    if (T == 0) return TF_OK;
+    if (!fwd || !bwd || T < 0 || H <= 0 || W <= 0) { set_error("tf_flow_finalise: invalid argument"); return TF_ERR_INVALID_ARGUMENT; }
+    const long long fe = (long long)H * W * 2;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (clamp_all && max_value > 0.f) {
+        for (int t0 = 0; t0 < T; t0 += 65535) {
+            const int nt = min(T - t0, 65535);
+            dim3 grid((unsigned)((fe + 255) / 256), nt);
+            // mirror flags only apply to the global first / last frame
+            flow_finalise_kernel<<<grid, 256, 0, s>>>(fwd + t0 * fe, bwd + t0 * fe, nt, fe, max_value, 1,
+                                                      mirror_first && t0 == 0, mirror_last && t0 + nt == T);
+        }
+    } else {
+        // only the two end frames change
+        dim3 grid((unsigned)((fe + 255) / 256), 1);
+        if (mirror_first)
+            flow_finalise_kernel<<<grid, 256, 0, s>>>(fwd, bwd, T == 1 ? 1 : 2, fe, 0.f, 0, 1, T == 1 && mirror_last);
+        if (mirror_last && T > 1)
+            flow_finalise_kernel<<<grid, 256, 0, s>>>(fwd + (T - 1) * fe, bwd + (T - 1) * fe, 1, fe, 0.f, 0, 0, 1);
+    }
+    return check_launch("tf_flow_finalise");
+}

@@ -1,0 +1,166 @@
+// K2: one pyramid level = convertTo(CV_32F) -> GaussianBlur(ksize, sigma, REFLECT_101) -> resize(INTER_LINEAR),
+// always from the full-resolution u8 image (OpenCV FarnebackOpticalFlow::calc, fastPyramids = false).
+// K6: bilinear flow up-sampling (resize(prevFlow) * 1/pyrScale).
+//
+// Only the source rows/columns the bilinear resize actually reads are blurred: pass A blurs vertically at the
+// (at most two) source rows of every destination row, pass B blurs those rows horizontally at the (at most two)
+// source columns of every destination pixel and combines the four values with OpenCV's resize weights.
+#include "tf_common.cuh"
+#include "farneback_internal.cuh"
+
+namespace tf {
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i;
+        if (i >= n) i = 2 * (n - 1) - i;
+    }
+    return i;
+}
+
+// cv::resize INTER_LINEAR source coordinate: index of the first tap and fp32 weight of the second
+__device__ __forceinline__ void resize_coord(int d, double scale, int src_n, int& i0, int& i1, float& f) {
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    int ix = (int)floorf(fx);
+    fx -= (float)ix;
+    if (ix < 0) { fx = 0.f; ix = 0; }
+    if (ix >= src_n - 1) { fx = 0.f; ix = src_n - 1; }
+    i0 = ix;
+    i1 = min(ix + 1, src_n - 1);
+    f = fx;
+}
+
+// pass A.  tmp: (n_img, h*rp, W) fp32, rp = rows per destination row (1 when h == H, else 2)
+__global__ void __launch_bounds__(256) blur_v_kernel(const uint8_t* __restrict__ q0, const uint8_t* __restrict__ q1,
+                                                     float* __restrict__ tmp, int H, int W, int h, int rp,
+                                                     double scale_y, BlurTaps taps) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    const int img = blockIdx.z;  // 2*pair + which
+    if (x >= W) return;
+    const uint8_t* src = ((img & 1) ? q1 : q0) + (long long)(img >> 1) * H * W;
+    int sy;
+    if (rp == 1) {
+        sy = r;
+    } else {
+        int y0, y1; float fy;
+        resize_coord(r >> 1, scale_y, H, y0, y1, fy);
+        sy = (r & 1) ? y1 : y0;
+    }
+    const int rad = taps.ksize >> 1;
+    float acc = 0.f;
+    for (int k = 0; k < taps.ksize; ++k) {
+        int yy = reflect101(sy + k - rad, H);
+        acc += taps.w[k] * (float)src[(long long)yy * W + x];
+    }
+    tmp[((long long)img * (h * rp) + r) * W + x] = acc;
+}
+
+// pass B.  out: (n_img, h, w) fp32
+__global__ void __launch_bounds__(256) blur_h_resize_kernel(const float* __restrict__ tmp, float* __restrict__ out, int W,
+                                                            int h, int w, int rp, double scale_x, double scale_y,
+                                                            int H, BlurTaps taps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int img = blockIdx.z;
+    if (i >= w) return;
+    const int rad = taps.ksize >> 1;
+    const float* rows = tmp + ((long long)img * (h * rp) + (long long)j * rp) * W;
+    float res;
+    if (w == W && rp == 1) {
+        float acc = 0.f;
+        for (int k = 0; k < taps.ksize; ++k) acc += taps.w[k] * rows[reflect101(i + k - rad, W)];
+        res = acc;
+    } else {
+        int x0, x1, y0, y1; float fx, fy;
+        resize_coord(i, scale_x, W, x0, x1, fx);
+        resize_coord(j, scale_y, H, y0, y1, fy);
+        const float* row0 = rows;
+        const float* row1 = rp == 2 ? rows + W : rows;
+        float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+        for (int k = 0; k < taps.ksize; ++k) {
+            const float wk = taps.w[k];
+            const int xa = reflect101(x0 + k - rad, W), xb = reflect101(x1 + k - rad, W);
+            b00 += wk * row0[xa];
+            b01 += wk * row0[xb];
+            b10 += wk * row1[xa];
+            b11 += wk * row1[xb];
+        }
+        const float r0 = b00 * (1.f - fx) + b01 * fx;
+        const float r1 = b10 * (1.f - fx) + b11 * fx;
+        res = r0 * (1.f - fy) + r1 * fy;
+    }
+    out[((long long)img * h + j) * w + i] = res;
+}
+
+// K6: dst (n_fields, h, w, 2) = resize_linear(src (n_fields, sh, sw, 2)) * mul ; zero-fill when src == nullptr
+__global__ void __launch_bounds__(256) flow_upsample_kernel(const float2* __restrict__ src, float2* __restrict__ dst, int sh,
+                                                            int sw, int h, int w, double scale_x, double scale_y,
+                                                            float mul) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int f = blockIdx.z;
+    if (i >= w) return;
+    float2 o = make_float2(0.f, 0.f);
+    if (src != nullptr) {
+        int x0, x1, y0, y1; float fx, fy;
+        resize_coord(i, scale_x, sw, x0, x1, fx);
+        resize_coord(j, scale_y, sh, y0, y1, fy);
+        const float2* s = src + (long long)f * sh * sw;
+        const float2 a = s[(long long)y0 * sw + x0], b = s[(long long)y0 * sw + x1];
+        const float2 c = s[(long long)y1 * sw + x0], d = s[(long long)y1 * sw + x1];
+        const float ax = a.x * (1.f - fx) + b.x * fx, ay = a.y * (1.f - fx) + b.y * fx;
+        const float cx = c.x * (1.f - fx) + d.x * fx, cy = c.y * (1.f - fx) + d.y * fx;
+        o.x = (ax * (1.f - fy) + cx * fy) * mul;
+        o.y = (ay * (1.f - fy) + cy * fy) * mul;
+    }
+    dst[((long long)f * h + j) * w + i] = o;
+}
+
+int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int H, int W, int h, int w, int ksize,
+                         double sigma, float* tmp, float* out, cudaStream_t s) {
+    BlurTaps taps;
+    taps.ksize = ksize;
+    if (ksize > kMaxBlurTaps) { set_error("pyramid: blur kernel too wide (%d)", ksize); return TF_ERR_UNSUPPORTED; }
+    if (sigma <= 0 && ksize == 3) {
+        taps.w[0] = 0.25f; taps.w[1] = 0.5f; taps.w[2] = 0.25f;
+    } else {
+        if (sigma <= 0) sigma = 0.3 * ((ksize - 1) * 0.5 - 1) + 0.8;
+        double sum = 0, v[kMaxBlurTaps];
+        for (int i = 0; i < ksize; ++i) {
+            double x = i - (ksize - 1) * 0.5;
+            v[i] = exp(-0.5 * x * x / (sigma * sigma));
+            sum += v[i];
+        }
+        for (int i = 0; i < ksize; ++i) taps.w[i] = (float)(v[i] / sum);
+    }
+    const int rp = (h == H) ? 1 : 2;
+    const double sx = (double)W / w, sy = (double)H / h;
+    const int n_img = 2 * n_pairs;
+    for (int z0 = 0; z0 < n_img; z0 += 65534) {
+        const int nz = min(n_img - z0, 65534);  // even, so image parity is preserved
+        dim3 ga(cdiv(W, 256), h * rp, nz);
+        blur_v_kernel<<<ga, 256, 0, s>>>(q0 + (long long)(z0 / 2) * H * W, q1 + (long long)(z0 / 2) * H * W,
+                                         tmp + (long long)z0 * h * rp * W, H, W, h, rp, sy, taps);
+        dim3 gb(cdiv(w, 256), h, nz);
+        blur_h_resize_kernel<<<gb, 256, 0, s>>>(tmp + (long long)z0 * h * rp * W, out + (long long)z0 * h * w, W, h, w, rp,
+                                                sx, sy, H, taps);
+    }
+    return check_launch("pyramid level");
+}
+
+int launch_flow_upsample(const float* src, float* dst, int n_fields, int sh, int sw, int h, int w, float mul,
+                         cudaStream_t s) {
+    const double sx = sw > 0 ? (double)sw / w : 1.0, sy = sh > 0 ? (double)sh / h : 1.0;
+    for (int z0 = 0; z0 < n_fields; z0 += 65535) {
+        const int nz = min(n_fields - z0, 65535);
+        dim3 g(cdiv(w, 256), h, nz);
+        flow_upsample_kernel<<<g, 256, 0, s>>>(
+            src ? reinterpret_cast<const float2*>(src) + (long long)z0 * sh * sw : nullptr,
+            reinterpret_cast<float2*>(dst) + (long long)z0 * h * w, sh, sw, h, w, sx, sy, mul);
+    }
+    return check_launch("flow upsample");
+}
+
+}  // namespace tf

@@ -1,0 +1,541 @@
+"""B200-native drop-in for ``tobac_flow.flow`` — the dense-flow hot path only.
+
+Mirrors the reference interface (``tobac_flow/flow.py:23-65`` ``create_flow``, ``:68-355`` ``Flow``,
+``:362-428`` ``calculate_flow``, ``:530-568`` ``smooth_flow_step``; contract ``tobac_flow/core/abstracts.py:10-84``):
+same names, argument meaning, defaults and exception types.  All arithmetic runs in the hand-written CUDA
+kernels of ``libtobacflow_b200.so`` through its C ABI (``include/tobac_flow_b200.h``); PyTorch is used only for
+device memory and streams.  There is no CPU fallback.
+
+Differences by design (device residency):
+* ``Flow`` keeps its vectors as CUDA tensors; ``.forward_flow`` / ``.backward_flow`` materialise numpy copies
+  lazily (the downstream ``watershed.py`` / ``label.py`` read them as numpy).
+* ``convolve`` / ``diff`` / ``sobel`` return numpy for numpy input and CUDA tensors for CUDA-tensor input, so
+  chained operators (``diff`` -> ``filtered_tdiff``) stay on the device.
+"""
+import ctypes
+from functools import partial
+from typing import Callable
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NativeError  # noqa: F401  (re-export)
+
+_INTERP = {"nearest": _lib.TF_NEAREST, "linear": _lib.TF_LINEAR, "cubic": _lib.TF_CUBIC}
+_REFERENCE_INTERP_NAMES = ["nearest", "linear", "cubic", "lanczos"]  # convolve.py:46-51
+_REFERENCE_MODELS = ["Farneback", "DeepFlow", "PCA", "SimpleFlow", "SparseToDense", "DIS", "DenseRLOF", "DualTVL1"]
+_NORMALISATIONS = ["linear", "log", "inverse_log", "z_score", "uniform", "local_linear"]
+
+_TORCH_DT = {torch.float32: _lib.TF_F32, torch.float64: _lib.TF_F64, torch.int32: _lib.TF_I32}
+
+
+def _default_structure():
+    s = np.zeros((3, 3, 3), bool)  # == ndi.generate_binary_structure(3, 1)
+    s[1, 1, :] = s[1, :, 1] = s[:, 1, 1] = True
+    return s
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise NativeError("tobac_flow_b200 needs a CUDA device (there is no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _interp_code(method: str) -> int:
+    if method not in _REFERENCE_INTERP_NAMES:
+        raise ValueError(f"method must be one of {_REFERENCE_INTERP_NAMES}")  # convolve.py:52-53
+    if method not in _INTERP:
+        raise NotImplementedError(f"interpolation '{method}' is not built in tobac_flow_b200 (nearest/linear/cubic are)")
+    return _INTERP[method]
+
+
+def _as_numpy(data):
+    if isinstance(data, torch.Tensor):
+        return None
+    if hasattr(data, "compute") and hasattr(data, "data") and not isinstance(data, np.ndarray):
+        data = data.compute().data  # xr.DataArray   (flow.py:405-406)
+    elif hasattr(data, "to_numpy"):
+        data = data.to_numpy()      # convolve.py:293-294
+    return np.asarray(data)
+
+
+def _to_device(data, dtype=None):
+    """numpy / DataArray-like / tensor -> contiguous CUDA tensor; returns (tensor, came_from_host)."""
+    dev = _device()
+    if isinstance(data, torch.Tensor):
+        t = data.to(dev)
+        host = not data.is_cuda
+    else:
+        a = np.ascontiguousarray(_as_numpy(data))
+        if a.dtype == np.bool_:
+            a = a.astype(np.int32)
+        t = torch.from_numpy(a).to(dev, non_blocking=False)
+        host = True
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous(), host
+
+
+def _dtype_code(np_dtype):
+    """``dtype=`` of the reference (a numpy dtype or None -> float64, np.full semantics) -> (torch dtype, code)."""
+    dt = np.dtype(np.float64 if np_dtype is None else np_dtype)
+    if dt == np.float32:
+        return torch.float32, _lib.TF_F32
+    if dt == np.float64:
+        return torch.float64, _lib.TF_F64
+    if dt == np.int32:
+        return torch.int32, _lib.TF_I32
+    raise NotImplementedError(f"dtype {dt} is not built in tobac_flow_b200 (float32, float64, int32 are)")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reducer recognition
+# ------------------------------------------------------------------------------------------------------------------
+def diff_func(x):
+    """The reducer of ``Flow.diff`` (tobac_flow/flow.py:182-186)."""
+    return np.nansum([x[2] - x[1], x[1] - x[0]], axis=0) * 1 / np.maximum(
+        np.sum([np.isfinite(x[2]), np.isfinite(x[0])], 0), 1)
+
+
+def _sobel_ref(direction):
+    w = np.array([1, 2, 1])
+    d = np.array([-1, 0, 1])
+    S = w[:, None, None] * w[None, :, None] * d[None, None, :]
+    ks = [k.ravel()[:, None, None] for k in (S, S.transpose(1, 2, 0), S.transpose(2, 0, 1))]
+
+    def f(x):
+        if direction == "uphill":
+            x = np.fmax(x - x[13], 0)
+        elif direction == "downhill":
+            x = np.fmin(x - x[13], 0)
+        else:
+            x = x - x[13]
+        return sum(np.nansum(x * k, 0) ** 2 for k in ks) ** 0.5
+    return f
+
+
+_CANDIDATES = [
+    (_lib.TF_RED_NANMEAN, None, lambda x: np.nanmean(x, 0)),
+    (_lib.TF_RED_NANMAX, None, lambda x: np.nanmax(x, 0)),
+    (_lib.TF_RED_NANMIN, None, lambda x: np.nanmin(x, 0)),
+    (_lib.TF_RED_ANY, None, lambda x: np.any(x, 0)),
+    (_lib.TF_RED_DIFF, 3, diff_func),
+    (_lib.TF_RED_SOBEL, 27, _sobel_ref(None)),
+    (_lib.TF_RED_SOBEL_UPHILL, 27, _sobel_ref("uphill")),
+    (_lib.TF_RED_SOBEL_DOWNHILL, 27, _sobel_ref("downhill")),
+]
+
+
+def recognise_reducer(func: Callable, n_taps: int, stack_dtype) -> int | None:
+    """Map a Python ``func=`` to a fused kernel reducer, or None if it is not one the library implements.
+
+    Callers of the reference pass anonymous lambdas (``lambda x: np.nanmean(x, 0)``, detection.py:53-55), so
+    identity checks are not enough: the callable is probed on two small seeded tap stacks containing NaNs and
+    matched, bit for bit, against the numpy definition of each built reducer.
+    """
+    if func is None:
+        return _lib.TF_RED_NONE
+    tagged = getattr(func, "_tf_reducer", None)
+    if tagged is not None:
+        return tagged
+    if isinstance(func, partial) and func.func is np.any and func.keywords == {"axis": 0} and not func.args:
+        return _lib.TF_RED_ANY
+    import warnings
+    rng = np.random.default_rng(20240229)
+    dt = np.dtype(np.float64 if stack_dtype is None else stack_dtype)
+    probes = []
+    for _ in range(2):
+        x = rng.standard_normal((n_taps, 3, 4)) * 10
+        x[rng.random(x.shape) < 0.25] = np.nan
+        x[:, 0, 0] = np.nan
+        x[rng.random(x.shape) < 0.1] = 0
+        if dt.kind in "iub":
+            x = np.nan_to_num(x).astype(dt)
+        else:
+            x = x.astype(dt)
+        probes.append(x)
+    with warnings.catch_warnings(), np.errstate(all="ignore"):
+        warnings.simplefilter("ignore")
+        try:
+            got = [np.asarray(func(p.copy())) for p in probes]
+        except Exception:
+            return None
+        for code, need, ref in _CANDIDATES:
+            if need is not None and need != n_taps:
+                continue
+            try:
+                want = [np.asarray(ref(p.copy())) for p in probes]
+            except Exception:
+                continue
+            if all(g.shape == w.shape and np.array_equal(g.astype(np.float64), w.astype(np.float64), equal_nan=True)
+                   for g, w in zip(got, want)):
+                return code
+    return None
+
+
+def _tag(code):
+    def deco(f):
+        f._tf_reducer = code
+        return f
+    return deco
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the stencil operator
+# ------------------------------------------------------------------------------------------------------------------
+def convolve_device(data: torch.Tensor, fwd: torch.Tensor, bwd: torch.Tensor, structure, method, fill_value,
+                    dtype, reducer: int, has_prev: bool = False, has_next: bool = False,
+                    out: torch.Tensor | None = None) -> torch.Tensor:
+    """Launch tf_sl_convolve on device tensors.
+
+    ``data`` is (T, H, W).  With ``has_prev`` / ``has_next`` the first / last frame of ``data`` is a halo frame
+    (time sharding): it is only read, and the flows/outputs then cover the T-1 / T-2 interior frames.
+    """
+    lib = _lib.load()
+    interp = _interp_code(method)
+    structure = np.asarray(structure)
+    assert structure.shape == (3, 3, 3), "Structure input must be a 3x3x3 array"  # convolve.py:290
+    n_taps = int(np.count_nonzero(structure))
+    out_t, stack_code = _dtype_code(dtype)
+    if data.dtype not in _TORCH_DT:
+        if data.dtype in (torch.int64, torch.int16, torch.int8, torch.uint8, torch.bool):
+            data = data.to(torch.int32)  # cv2's binding narrows wider integers the same way
+        elif data.dtype in (torch.float16, torch.bfloat16):
+            data = data.to(torch.float32)
+        else:
+            raise NotImplementedError(f"operand dtype {data.dtype} is not supported")
+    data = data.contiguous()
+    T_all, H, W = data.shape
+    n_frames = T_all - int(bool(has_prev)) - int(bool(has_next))
+    if tuple(fwd.shape) != (n_frames, H, W, 2) or tuple(bwd.shape) != (n_frames, H, W, 2):
+        raise AssertionError("Data input must have the same shape as the Flow object")
+    fwd = fwd.contiguous()
+    bwd = bwd.contiguous()
+    shape = (n_frames, H, W) if reducer != _lib.TF_RED_NONE else (n_taps, n_frames, H, W)
+    if out is None:
+        out = torch.empty(shape, dtype=out_t, device=data.device)
+    else:
+        assert tuple(out.shape) == shape and out.dtype == out_t and out.is_contiguous()
+    if n_frames == 0:
+        return out
+    cur0 = data.data_ptr() + (data.element_size() * H * W if has_prev else 0)
+    rc = lib.tf_sl_convolve(cur0, n_frames, int(bool(has_prev)), int(bool(has_next)), fwd.data_ptr(), bwd.data_ptr(),
+                            out.data_ptr(), n_frames * H * W, H, W, _TORCH_DT[data.dtype], stack_code, interp,
+                            reducer, _lib.structure_bytes(structure), float(fill_value), _stream())
+    _lib.check(rc, "tf_sl_convolve")
+    return out
+
+
+class Flow:
+    """Semi-Lagrangian operators on optical-flow vectors (drop-in for ``tobac_flow.flow.Flow``)."""
+
+    def __init__(self, forward_flow, backward_flow) -> None:
+        if tuple(forward_flow.shape) != tuple(backward_flow.shape):
+            raise ValueError("Forward and backward flow vector arrays must have the same shape")
+        if forward_flow.shape[-1] != 2:
+            raise ValueError("Flow vectors must have a size of 2 in the trailing dimension")
+        self.shape = tuple(forward_flow.shape[:-1])
+        self._fwd_np = forward_flow if isinstance(forward_flow, np.ndarray) else None
+        self._bwd_np = backward_flow if isinstance(backward_flow, np.ndarray) else None
+        self._fwd_t = forward_flow if isinstance(forward_flow, torch.Tensor) else None
+        self._bwd_t = backward_flow if isinstance(backward_flow, torch.Tensor) else None
+        if self._fwd_np is None and self._fwd_t is None:
+            self._fwd_np = np.asarray(forward_flow)
+        if self._bwd_np is None and self._bwd_t is None:
+            self._bwd_np = np.asarray(backward_flow)
+
+    # -- flow vectors ------------------------------------------------------------------------------
+    @property
+    def forward_flow(self) -> np.ndarray:
+        if self._fwd_np is None:
+            self._fwd_np = self._fwd_t.detach().cpu().numpy()
+        return self._fwd_np
+
+    @property
+    def backward_flow(self) -> np.ndarray:
+        if self._bwd_np is None:
+            self._bwd_np = self._bwd_t.detach().cpu().numpy()
+        return self._bwd_np
+
+    @property
+    def forward_flow_device(self) -> torch.Tensor:
+        if self._fwd_t is None or not self._fwd_t.is_cuda:
+            src = self._fwd_t if self._fwd_t is not None else self._fwd_np
+            self._fwd_t = _to_device(src, torch.float32)[0]
+        return self._fwd_t
+
+    @property
+    def backward_flow_device(self) -> torch.Tensor:
+        if self._bwd_t is None or not self._bwd_t.is_cuda:
+            src = self._bwd_t if self._bwd_t is not None else self._bwd_np
+            self._bwd_t = _to_device(src, torch.float32)[0]
+        return self._bwd_t
+
+    @property
+    def flow(self):
+        return self.forward_flow, self.backward_flow
+
+    def __getitem__(self, items) -> "Flow":
+        f = self._fwd_t[items] if self._fwd_t is not None else self._fwd_np[items]
+        b = self._bwd_t[items] if self._bwd_t is not None else self._bwd_np[items]
+        return Flow(f, b)
+
+    # -- operators ---------------------------------------------------------------------------------
+    def convolve(self, data, structure=None, method: str = "linear", fill_value: float = np.nan,
+                 dtype: type = np.float32, func: Callable | None = None):
+        """``Flow.convolve`` (tobac_flow/flow.py:105-157 -> tobac_flow/convolve.py:248-348)."""
+        if structure is None:
+            structure = _default_structure()
+        assert tuple(data.shape) == self.shape, "Data input must have the same shape as the Flow object"
+        structure = np.asarray(structure)
+        assert structure.shape == (3, 3, 3), "Structure input must be a 3x3x3 array"
+        _interp_code(method)
+        n_taps = int(np.count_nonzero(structure))
+        t, from_host = _to_device(data)
+        reducer = recognise_reducer(func, n_taps, dtype)
+        if reducer is None:
+            res = self._convolve_python_func(t, structure, method, fill_value, dtype, func)
+        else:
+            res = convolve_device(t, self.forward_flow_device, self.backward_flow_device, structure, method,
+                                  fill_value, dtype, reducer)
+        return res.cpu().numpy() if from_host else res
+
+    def _convolve_python_func(self, t, structure, method, fill_value, dtype, func):
+        """Compatibility path for arbitrary Python reducers: the tap stack of each step is gathered by the
+        CUDA kernel and ``func`` is applied to it on the host (convolve.py:316-331, 346-347)."""
+        T = t.shape[0]
+        out_t, _ = _dtype_code(dtype)
+        res = torch.full(tuple(t.shape), float(fill_value) if out_t.is_floating_point else int(fill_value),
+                         dtype=out_t, device=t.device)
+        fwd, bwd = self.forward_flow_device, self.backward_flow_device
+        for i in range(T):
+            lo, hi = max(i - 1, 0), min(i + 2, T)
+            stack = convolve_device(t[lo:hi], fwd[i:i + 1], bwd[i:i + 1], structure, method, fill_value, dtype,
+                                    _lib.TF_RED_NONE, has_prev=i > 0, has_next=i < T - 1)
+            r = np.asarray(func(stack[:, 0].cpu().numpy()))
+            res[i] = torch.from_numpy(np.ascontiguousarray(r)).to(device=t.device, dtype=out_t)
+        if t.dtype.is_floating_point:
+            res[torch.isnan(t)] = float(fill_value) if out_t.is_floating_point else int(fill_value)
+        return res
+
+    def diff(self, data, method: str = "linear", dtype: type = np.float32):
+        """``Flow.diff`` (tobac_flow/flow.py:159-191)."""
+        diff_struct = np.zeros([3, 3, 3])
+        diff_struct[:, 1, 1] = 1
+        return self.convolve(data, structure=diff_struct, func=_DIFF, method=method, dtype=dtype)
+
+    def sobel(self, data, method: str = "linear", dtype: type = None, fill_value: float = np.nan,
+              direction: str | None = None):
+        """``Flow.sobel`` (tobac_flow/flow.py:193-234 -> tobac_flow/sobel.py:89-143); dtype=None -> float64."""
+        from .sobel import sobel_reducer
+        return self.convolve(data, structure=np.ones((3, 3, 3), bool), method=method, fill_value=fill_value,
+                             dtype=dtype, func=sobel_reducer(direction))
+
+    # -- downstream consumers (out of the hot-path scope; they stay the reference's own numpy code) -----------------
+    def _delegate(self, name, *args, **kwargs):
+        try:
+            import tobac_flow.flow as ref  # the reference package, when installed next to this one
+        except Exception as e:  # pragma: no cover
+            raise NotImplementedError(
+                f"Flow.{name} is outside the dense-flow hot path; it delegates to the reference's tobac_flow.{name} "
+                "which is not importable here") from e
+        return getattr(ref.Flow, name)(self, *args, **kwargs)
+
+    def watershed(self, field, markers, mask=None, connectivity=1):
+        return self._delegate("watershed", field, markers, mask=mask, connectivity=connectivity)
+
+    def label(self, data, structure=None, dtype: type = np.int32, overlap: float = 0, absolute_overlap: int = 1,
+              subsegment_shrink: float = 0, peak_min_distance: int = 5):
+        if structure is None:
+            structure = _default_structure()
+        return self._delegate("label", data, structure=structure, dtype=dtype, overlap=overlap,
+                              absolute_overlap=absolute_overlap, subsegment_shrink=subsegment_shrink,
+                              peak_min_distance=peak_min_distance)
+
+    def link_overlap(self, data, structure=None, dtype: type = np.int32, overlap: float = 0,
+                     absolute_overlap: int = 1):
+        if structure is None:
+            structure = _default_structure()
+        return self._delegate("link_overlap", data, structure=structure, dtype=dtype, overlap=overlap,
+                              absolute_overlap=absolute_overlap)
+
+
+_DIFF = _tag(_lib.TF_RED_DIFF)(diff_func)
+
+try:  # register against the reference ABC when the reference is importable (it is optional)
+    from tobac_flow.core import AbstractFlow as _AbstractFlow  # type: ignore
+
+    _AbstractFlow.register(Flow)
+except Exception:  # pragma: no cover
+    pass
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# flow construction
+# ------------------------------------------------------------------------------------------------------------------
+def _check_model(model: str, vr_steps: int):
+    if model not in _REFERENCE_MODELS:
+        raise ValueError(  # utils/flow_utils.py:72-75
+            "'model' parameter must be one of: 'Farneback', 'DeepFlow', 'PCA', 'SimpleFlow', 'SparseToDense', "
+            "'DIS', 'DenseRLOF', 'DualTVL1'")
+    if model != "Farneback":
+        raise NotImplementedError(f"optical-flow model '{model}' is not built in tobac_flow_b200 (only 'Farneback')")
+    if vr_steps and vr_steps > 0:
+        raise NotImplementedError("variational refinement (vr_steps > 0) is not built in tobac_flow_b200 yet")
+
+
+def _pair_batch(n_pairs: int, H: int, W: int, params) -> int:
+    """Pairs per launch batch: as many as fit comfortably in free HBM, capped so coarse levels still fill 148 SMs."""
+    per_pair = _lib.workspace_bytes(1, H, W, params) + 2 * H * W
+    free, _ = torch.cuda.mem_get_info()
+    by_mem = max(1, int(free * 0.6) // per_pair)
+    by_px = max(1, (96 << 20) // (H * W))
+    return max(1, min(n_pairs, by_mem, by_px))
+
+
+def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Tensor, smoothing_passes: int = 0,
+                          interp_method: str = "linear", max_value: float | None = None,
+                          next_frames: torch.Tensor | None = None, batch: int | None = None) -> None:
+    """Fill ``fwd[i]`` and ``bwd[i + 1]`` for every consecutive pair of ``frames`` (device tensors, in place).
+
+    ``frames`` (T, H, W) float32; ``fwd``/``bwd`` (>= T, H, W, 2) float32.  With ``next_frames`` the pairs are
+    (frames[i], next_frames[i]) and results go to fwd[i], bwd[i + 1] for every i (``calculate_flow_2``).
+    ``max_value`` fuses the clamp of ``create_flow`` into the last kernel when no smoothing follows.
+    """
+    lib = _lib.load()
+    T, H, W = frames.shape
+    n_pairs = T - 1 if next_frames is None else T
+    if n_pairs <= 0:
+        return
+    interp = _interp_code(interp_method)
+    fuse_clamp = (max_value is not None) and smoothing_passes == 0
+    params = _lib.default_params(max_value if fuse_clamp else 0.0)
+    nb = batch or _pair_batch(n_pairs, H, W, params)
+    dev = frames.device
+    q0 = torch.empty((nb, H, W), dtype=torch.uint8, device=dev)
+    q1 = torch.empty((nb, H, W), dtype=torch.uint8, device=dev)
+    mm = torch.empty((2 * nb,), dtype=torch.float32, device=dev)
+    ws_bytes = _lib.workspace_bytes(nb, H, W, params)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    tmp_f = tmp_b = None
+    if smoothing_passes > 0:
+        tmp_f = torch.empty((nb, H, W, 2), dtype=torch.float32, device=dev)
+        tmp_b = torch.empty((nb, H, W, 2), dtype=torch.float32, device=dev)
+    hw = H * W
+    es = frames.element_size()
+    st = _stream()
+    for p0 in range(0, n_pairs, nb):
+        n = min(nb, n_pairs - p0)
+        f0 = frames.data_ptr() + p0 * hw * es
+        f1 = (frames.data_ptr() + (p0 + 1) * hw * es) if next_frames is None else (next_frames.data_ptr() + p0 * hw * es)
+        _lib.check(lib.tf_pair_normalise_u8(f0, f1, hw, q0.data_ptr(), q1.data_ptr(), n, H, W, mm.data_ptr(), st),
+                   "tf_pair_normalise_u8")
+        fo = fwd.data_ptr() + p0 * hw * 2 * 4
+        bo = bwd.data_ptr() + (p0 + 1) * hw * 2 * 4
+        _lib.check(lib.tf_farneback_pairs(q0.data_ptr(), q1.data_ptr(), fo, hw * 2, bo, hw * 2, n, H, W,
+                                          ctypes.byref(params), ws.data_ptr(), ws_bytes, st), "tf_farneback_pairs")
+        for _ in range(smoothing_passes):
+            _lib.check(lib.tf_smooth_flow_step(fo, bo, tmp_f.data_ptr(), tmp_b.data_ptr(), hw * 2, n, H, W, interp, st),
+                       "tf_smooth_flow_step")
+            fwd[p0:p0 + n].copy_(tmp_f[:n])
+            bwd[p0 + 1:p0 + 1 + n].copy_(tmp_b[:n])
+
+
+def finalise_flow_device(fwd: torch.Tensor, bwd: torch.Tensor, max_value: float | None, clamp_all: bool,
+                         mirror_first: bool = True, mirror_last: bool = True) -> None:
+    T, H, W, _ = fwd.shape
+    _lib.check(_lib.load().tf_flow_finalise(fwd.data_ptr(), bwd.data_ptr(), T, H, W,
+                                            float(max_value) if max_value is not None else 0.0, int(clamp_all),
+                                            int(mirror_first), int(mirror_last), _stream()), "tf_flow_finalise")
+
+
+def _select_normalisation(method: str):
+    if method not in _NORMALISATIONS:  # normalisation_utils.py:130-133
+        raise ValueError(f"{method} not an acceptable normalisation method, method must be one of {_NORMALISATIONS}")
+    if method != "linear":
+        raise NotImplementedError(f"normalisation '{method}' is not built in tobac_flow_b200 (only 'linear')")
+
+
+def _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_method, normalisation_method,
+                            max_value, data_b=None):
+    _check_model(model, vr_steps)
+    _select_normalisation(normalisation_method)
+    _interp_code(interp_method)
+    frames, _ = _to_device(data, torch.float32)
+    if frames.dim() != 3:
+        raise ValueError("data must have shape (t, y, x)")
+    frames_b = None
+    if data_b is not None:
+        frames_b, _ = _to_device(data_b, torch.float32)
+    T, H, W = frames.shape
+    fwd = torch.full((T, H, W, 2), float("nan"), dtype=torch.float32, device=frames.device)
+    bwd = torch.full((T, H, W, 2), float("nan"), dtype=torch.float32, device=frames.device)
+    if frames_b is None:
+        calculate_flow_device(frames, fwd, bwd, smoothing_passes, interp_method, max_value)
+    else:
+        # calculate_flow_2 (flow.py:431-496): pairs (a[i], b[i]) for i < T-1
+        calculate_flow_device(frames[:T - 1], fwd, bwd, smoothing_passes, interp_method, max_value,
+                              next_frames=frames_b[:T - 1])
+    clamp_all = max_value is not None and smoothing_passes > 0
+    finalise_flow_device(fwd, bwd, max_value, clamp_all)
+    return fwd, bwd
+
+
+def calculate_flow(data, model: str = "Farneback", vr_steps: int = 0, smoothing_passes: int = 0,
+                   interp_method: str = "linear", normalisation_method: str = "linear", **normalisation_kwargs):
+    """``calculate_flow`` (tobac_flow/flow.py:362-428): returns (forward_flow, backward_flow) numpy arrays."""
+    if normalisation_kwargs:
+        raise NotImplementedError("normalisation keyword arguments are not supported by the 'linear' method here")
+    fwd, bwd = _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_method,
+                                       normalisation_method, None)
+    return fwd.cpu().numpy(), bwd.cpu().numpy()
+
+
+def calculate_flow_2(a, b, model: str = "Farneback", vr_steps: int = 0, smoothing_passes: int = 0,
+                     normalisation_method: str = "linear", **normalisation_kwargs):
+    """``calculate_flow_2`` (tobac_flow/flow.py:431-496)."""
+    if normalisation_kwargs:
+        raise NotImplementedError("normalisation keyword arguments are not supported by the 'linear' method here")
+    fwd, bwd = _calculate_flow_tensors(a, model, vr_steps, smoothing_passes, "linear", normalisation_method, None,
+                                       data_b=b)
+    return fwd.cpu().numpy(), bwd.cpu().numpy()
+
+
+def create_flow(data, model: str = "Farneback", vr_steps: int = 0, smoothing_passes: int = 0,
+                interp_method: str = "linear", max_value=20) -> Flow:
+    """``create_flow`` (tobac_flow/flow.py:23-65): flow vectors for ``data`` (t, y, x), clamped to +-max_value.
+
+    The returned ``Flow`` keeps the vectors on the GPU.
+    """
+    fwd, bwd = _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_method, "linear", max_value)
+    return Flow(fwd, bwd)
+
+
+def smooth_flow_step(forward_flow, backward_flow, method: str = "linear"):
+    """``smooth_flow_step`` (tobac_flow/flow.py:530-568) for one (H, W, 2) pair of fields."""
+    interp = _interp_code(method)
+    f, host = _to_device(forward_flow, torch.float32)
+    b, _ = _to_device(backward_flow, torch.float32)
+    H, W, _two = f.shape
+    fo, bo = torch.empty_like(f), torch.empty_like(b)
+    _lib.check(_lib.load().tf_smooth_flow_step(f.data_ptr(), b.data_ptr(), fo.data_ptr(), bo.data_ptr(), H * W * 2, 1,
+                                               H, W, interp, _stream()), "tf_smooth_flow_step")
+    return (fo.cpu().numpy(), bo.cpu().numpy()) if host else (fo, bo)
+
+
+def pair_to_8bit(frame0, frame1):
+    """``to_8bit(linear_norm(stack), 0, 1)`` for one pair (normalisation_utils.py:59-72, 10-33)."""
+    a, host = _to_device(np.stack([_as_numpy(frame0), _as_numpy(frame1)]) if not isinstance(frame0, torch.Tensor)
+                         else torch.stack([frame0, frame1]), torch.float32)
+    _, H, W = a.shape
+    q = torch.empty((2, H, W), dtype=torch.uint8, device=a.device)
+    mm = torch.empty((2,), dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().tf_pair_normalise_u8(a.data_ptr(), a.data_ptr() + H * W * 4, H * W, q.data_ptr(),
+                                                q.data_ptr() + H * W, 1, H, W, mm.data_ptr(), _stream()),
+               "tf_pair_normalise_u8")
+    return (q[0].cpu().numpy(), q[1].cpu().numpy()) if host else (q[0], q[1])
