@@ -110,10 +110,14 @@ def test_flow_vs_oracle_odd_sizes(tfb, shape):
     assert_flow_close(f.backward_flow, ref_b, 2e-3, 2e-2)
 
 
-def test_identical_frames_give_zero_flow(tfb):
+def test_identical_frames_match_opencv_and_batching_is_deterministic(tfb):
     bt = synthetic.bt_sequence(1, 96, 128, seed=3, nans=False)
     f = tfb.create_flow(np.repeat(bt, 3, 0))
-    assert np.abs(f.forward_flow).max() < 1e-4 and np.abs(f.backward_flow).max() < 1e-4
+    # OpenCV itself is not zero here (near the borders its out-of-image branch drops the R1 term); the two pairs
+    # of the batch must agree bit for bit
+    assert np.array_equal(f.forward_flow[0], f.forward_flow[1])
+    q0, q1 = ops.pair_to_u8(bt[0], bt[0])
+    assert_flow_close(f.forward_flow[0], farneback_np.farneback(q0, q1), 1e-4, 1e-3)
 
 
 def test_clamp_and_calculate_flow(tfb):
