@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""Benchmark of the dense-flow hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A *step* is one pass of the hot path over one rank's batch of synthetic input: the 288-frame, 1500 x 2500
+GOES-CONUS-shaped brightness-temperature day of BASELINE.json configs[1] — forward+backward Farneback flow for
+every consecutive pair (normalise, quantise, 6-level pyramid, 10 iterations per level, clamp, end rules) plus
+``Flow.diff``, ``Flow.sobel`` (linear) and ``Flow.convolve`` (7-tap stack) on every frame.  With N GPUs the series
+is 288*N frames, time-sharded one day per rank with NCCL point-to-point halo exchange (weak scaling).
+
+``value``   frames/s with the inputs resident in HBM (CUDA events, max over ranks).
+``e2e``     the same unit of work through the public numpy API (create_flow / Flow.diff / sobel / convolve) with the
+            input in pinned host memory and every result copied back to the host inside the timed region, on a
+            bounded number of frames of the same shape.
+``roofline`` the dominant kernel (the fused Farneback iteration at the full-resolution level): algorithmic bytes
+            (56 B per pixel-iteration) / its CUDA-event time measured live during the timed steps.
+``cpu_baseline`` the reference's CPU implementation of the same unit of work (OpenCV Farneback + cv2.remap through
+            the oracle's restatement of the reference's Python) timed on this box's host cores on a bounded sample.
+
+``--impl reference`` times only that CPU implementation, with all host cores (a process pool over independent
+frames of work), and prints the same JSON line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/s (fwd+bwd flow + flow-convolve), GOES CONUS 1500x2500"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=288, help="frames per rank (BASELINE configs[1]: 288)")
+    ap.add_argument("--height", type=int, default=1500)
+    ap.add_argument("--width", type=int, default=2500)
+    ap.add_argument("--e2e-frames", type=int, default=24)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-workers", type=int, default=0)
+    return ap.parse_args()
+
+
+def level_sizes(H, W):
+    """OpenCV's level plan (coarsest first) — host arithmetic only."""
+    k, scale = 0, 1.0
+    while k < 5:
+        scale *= 0.5
+        if W * scale < 32 or H * scale < 32:
+            break
+        k += 1
+    out = []
+    for kk in range(k, -1, -1):
+        s = 0.5 ** kk
+        out.append((int(np.rint(H * s)), int(np.rint(W * s))))
+    return out
+
+
+def algorithmic_bytes_per_frame(H, W):
+    """B_frame = (140 + 2L) N + 1196 S."""
+    lv = level_sizes(H, W)
+    N = H * W
+    S = sum(h * w for h, w in lv)
+    return (140 + 2 * len(lv)) * N + 1196 * S, len(lv), S
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU reference arm (the only place outside tests/smoke where oracle/ is executed)
+# ----------------------------------------------------------------------------------------------------------------
+_CPU_FRAME_CACHE = {}
+
+
+def _cpu_frames(H, W, t_centre, seed=1234):
+    """Three consecutive synthetic frames (cached per worker process so input generation is not timed twice)."""
+    key = (H, W, t_centre, seed)
+    if key not in _CPU_FRAME_CACHE:
+        from tobac_flow_b200 import synthetic
+        base = synthetic.base_field(H, W, seed)
+        T = 288
+        cores = synthetic.core_table(T, H, W, seed)
+        plan = synthetic.nan_plan(T, H, W, seed)
+        _CPU_FRAME_CACHE.clear()
+        _CPU_FRAME_CACHE[key] = np.stack([synthetic.bt_frame(base, t, cores, plan, T)
+                                          for t in (t_centre - 1, t_centre, t_centre + 1)])
+    return _CPU_FRAME_CACHE[key]
+
+
+def _cpu_prime(args):
+    H, W, t_centre, _ = args
+    _cpu_frames(H, W, t_centre)
+    time.sleep(0.2)   # keep this worker busy so every worker of the pool receives one priming job
+    return 0
+
+
+def _cpu_frame_of_work(args):
+    """One frame of work on the CPU exactly as the reference computes it: one pair flow (fwd+bwd) + the three
+    stencils on the middle frame of a 3-frame window."""
+    H, W, t_centre, threads = args
+    from oracle import flow_ops as ops
+    backend = "cv2" if ops.have_cv2() else "numpy"
+    if backend == "cv2":
+        import cv2
+        cv2.setNumThreads(threads)
+    bt = _cpu_frames(H, W, t_centre)
+    t0 = time.perf_counter()
+    fwd, bwd = ops.create_flow(bt[:2], backend=backend)              # one pair, both directions
+    t1 = time.perf_counter()
+    # the three stencils on the middle frame only (convolve.py's per-step body), fed with the pair's fields
+    ff, bf = fwd[1], bwd[1]
+    s_diff = np.zeros((3, 3, 3)); s_diff[:, 1, 1] = 1
+    s_cross = np.zeros((3, 3, 3)); s_cross[1, 1, :] = s_cross[1, :, 1] = s_cross[:, 1, 1] = 1
+    d = ops.diff_reducer(ops.tap_stack(bt[0], bt[1], bt[2], ff, bf, s_diff, "linear", np.float32, np.nan, backend))
+    s = ops.sobel_reducer(None)(ops.tap_stack(bt[0], bt[1], bt[2], ff, bf, np.ones((3, 3, 3)), "linear", np.float64,
+                                              np.nan, backend))
+    c = ops.tap_stack(bt[0], bt[1], bt[2], ff, bf, s_cross, "linear", np.float32, np.nan, backend)
+    t2 = time.perf_counter()
+    return (t1 - t0), (t2 - t1), float(np.nansum(d) + np.nansum(s) + np.nansum(c))
+
+
+def cpu_baseline_single(H, W):
+    from oracle import flow_ops as ops
+    import multiprocessing as mp
+    threads = os.cpu_count() or 1
+    t_pair, t_stencil, _ = _cpu_frame_of_work((H, W, 10, -1))
+    backend = "cv2" if ops.have_cv2() else "numpy"
+    cores = 1
+    if backend == "cv2":
+        import cv2
+        cores = cv2.getNumThreads()
+    return {
+        "value": 1.0 / (t_pair + t_stencil), "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": (f"1 pair (fwd+bwd Farneback) + diff/sobel/convolve on 1 frame of {H}x{W}; reference Python "
+                   f"restated in oracle/flow_ops.py calling {'OpenCV ' + __import__('cv2').__version__ if backend == 'cv2' else 'the numpy restatement'}"
+                   f"; single process as the reference runs it; pair {t_pair:.2f} s + stencils {t_stencil:.2f} s per frame"),
+        "host_cpus": threads,
+    }
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation with all host cores; each step = one frame of work per worker."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import flow_ops as ops
+    H, W = args.height, args.width
+    ncpu = os.cpu_count() or 1
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    per_worker = 40 * H * W * 8 + (1 << 30)      # tap stacks + temporaries of the 27-tap float64 sobel
+    workers = args.ref_workers or max(1, min(ncpu, int(avail * 0.6 // per_worker), 64))
+    ctx = mp.get_context("spawn")
+    times = []
+    with ctx.Pool(workers) as pool:
+        jobs = [(H, W, 10, 1) for i in range(workers)]
+        pool.map(_cpu_prime, jobs, chunksize=1)     # untimed: synthesize (and cache) the input frames in every worker
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_frame_of_work, jobs)
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = workers / (ms / 1e3)
+    backend = "cv2" if ops.have_cv2() else "numpy"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"GOES CONUS-shaped synthetic BT {H}x{W}: per step, {workers} independent frames of work "
+                               "(1 pair fwd+bwd Farneback + diff + sobel + 7-tap convolve each) on the host CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": f"{workers} worker processes x 1 frame of work per step, cv2 threads = 1 per worker, "
+                                   f"backend {backend}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the B200 arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from tobac_flow_b200 import _lib, synthetic
+    from tobac_flow_b200 import distributed as D
+    import tobac_flow_b200 as tfb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    T, H, W = args.frames, args.height, args.width
+    N = H * W
+    # ---- synthetic input, resident in HBM: this rank's day of the 288*world-frame series --------------------------
+    base = synthetic.base_field(H, W, 1234)
+    cores = synthetic.core_table(T * world, H, W, 1234)
+    plan = synthetic.nan_plan(T * world, H, W, 1234)
+    base_t = torch.as_tensor(base, device=dev)
+    shard = D.Shard(torch.empty((T + 2, H, W), dtype=torch.float32, device=dev), rank, world)
+    for i in range(T):
+        shard.buf[1 + i] = synthetic.bt_frame(base_t, rank * T + i, cores, plan, T * world)
+    shard.buf[0] = float("nan")
+    shard.buf[-1] = float("nan")
+
+    fwd = torch.empty((T, H, W, 2), dtype=torch.float32, device=dev)
+    bwd = torch.empty((T + 1, H, W, 2), dtype=torch.float32, device=dev)
+    out_diff = torch.empty((T, H, W), dtype=torch.float32, device=dev)
+    out_sobel = torch.empty((T, H, W), dtype=torch.float64, device=dev)
+    out_conv = torch.empty((7, T, H, W), dtype=torch.float32, device=dev)
+    s_diff = np.zeros((3, 3, 3)); s_diff[:, 1, 1] = 1
+    s_full = np.ones((3, 3, 3))
+    s_cross = np.zeros((3, 3, 3)); s_cross[1, 1, :] = s_cross[1, :, 1] = s_cross[:, 1, 1] = 1
+
+    def step():
+        fl = D.create_flow_sharded(shard, max_value=20, fwd=fwd, bwd=bwd)          # halo exchange inside
+        fl.convolve(shard, s_diff, reducer=_lib.TF_RED_DIFF, exchange=False, out=out_diff)
+        fl.convolve(shard, s_full, dtype=None, reducer=_lib.TF_RED_SOBEL, exchange=False, out=out_sobel)
+        fl.convolve(shard, s_cross, reducer=_lib.TF_RED_NONE, exchange=False, out=out_conv)
+        return fl
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    _lib.profile_reset()
+    _lib.profile_enable(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = T * world / (ms_per_step / 1e3)
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
+    peak, peak_src = measured_peak()
+    dom = prof["fb_iter_fullres"]
+    achieved = dom["bytes"] / 1e9 / (dom["ms"] / 1e3) if dom["ms"] > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("fb_iter_fullres_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    b_frame, L, S = algorithmic_bytes_per_frame(H, W)
+    total_kernel_ms = sum(v["ms"] for v in prof.values())
+    launches = int(sum(v["launches"] for v in prof.values()))
+    roofline = {
+        "bound": "hbm", "kernel": "fb_iter_kernel<6> at the full-resolution level", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "bytes_per_launch": dom["bytes"] / max(dom["launches"], 1), "avg_launch_ms": dom["ms"] / max(dom["launches"], 1),
+        "share_of_step_kernel_time": dom["ms"] / total_kernel_ms if total_kernel_ms else None,
+        "whole_step": {"algorithmic_bytes_per_frame": b_frame, "achieved": value / world * b_frame / 1e9,
+                       "frac": value / world * b_frame / 1e9 / peak},
+        "per_class": {k: {"ms_per_step": v["ms"] / args.steps, "GBps": (v["bytes"] / 1e9 / (v["ms"] / 1e3)) if v["ms"] > 0 else None,
+                          "launches_per_step": v["launches"] / args.steps} for k, v in prof.items() if v["launches"]},
+    }
+
+    # ---- end to end through the public numpy API with host buffers ---------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        Te = min(args.e2e_frames, T)
+        host_in = torch.empty((Te, H, W), dtype=torch.float32, pin_memory=True)
+        host_in.copy_(shard.buf[1:1 + Te])
+        torch.cuda.synchronize()
+        host_np = host_in.numpy()
+
+        def e2e_step():
+            fl = tfb.create_flow(host_np)                  # H2D inside
+            d = fl.diff(host_np)                           # H2D + D2H inside
+            s = fl.sobel(host_np)
+            c = fl.convolve(host_np)
+            return float(d[0, 0, 0]) + float(s[0, 0, 0]) + float(c[0, 0, 0, 0])
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": Te * world / dt, "unit": UNIT, "h2d_bytes_per_step": 4 * Te * N * 4,
+               "d2h_bytes_per_step": Te * N * (4 + 8 + 28), "frames_per_step": Te,
+               "note": "create_flow + diff + sobel + convolve via the numpy API; input pinned, each operator uploads "
+                       "its operand and returns a host array; flows stay on the device (Flow keeps them resident)"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline_single(H, W)
+        except Exception as e:  # pragma: no cover
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"GOES-16 ABI CONUS-shaped synthetic BT, {T} frames x {H}x{W} per GPU "
+                                   f"({T * world} frames time-sharded over {world} GPU(s), NCCL p2p halos): fwd+bwd "
+                                   "Farneback per pair + Flow.diff + Flow.sobel(linear, f64) + Flow.convolve(7-tap stack)",
+                       "frames_per_gpu": T, "height": H, "width": W, "pyramid_levels": L,
+                       "l2": "inputs (4.3 GB of frames per GPU) are far larger than the 126 MB L2; no explicit flush"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches // max(args.steps, 1) * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -142,6 +142,18 @@ int tf_sl_convolve(const void* cur0, int n_frames, int has_prev, int has_next, c
                    int stack_dtype, int interp, int reducer, const uint8_t* structure27 /* host */,
                    double fill, void* stream);
 
+/*
+ * Launch accounting (used by bench.py; no reference counterpart).  Kernel classes:
+ *   0 normalise, 1 pyramid, 2 polyexp, 3 flow upsample, 4 Farneback iteration (coarser levels),
+ *   5 Farneback iteration at the full-resolution level, 6 semi-Lagrangian gather, 7 flow smoothing, 8 finalise.
+ * Launch counts and algorithmic bytes are always accumulated; device time is measured with CUDA events recorded
+ * on the launching stream while profiling is enabled.  tf_profile_read synchronises on the recorded events.
+ */
+int tf_profile_enable(int on);
+int tf_profile_reset(void);
+int tf_profile_read(int kernel_class, double* total_ms /* host */, double* total_bytes /* host */,
+                    long long* launches /* host */);
+
 #ifdef __cplusplus
 }
 #endif

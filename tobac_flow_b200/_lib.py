@@ -20,8 +20,11 @@ TF_NEAREST, TF_LINEAR, TF_CUBIC = 0, 1, 2
 EXPORTS = (
     "tf_version", "tf_last_error", "tf_fb_default_params", "tf_fb_level_plan", "tf_fb_poly_constants",
     "tf_farneback_workspace_bytes", "tf_pair_normalise_u8", "tf_farneback_pairs", "tf_smooth_flow_step",
-    "tf_flow_finalise", "tf_sl_convolve",
+    "tf_flow_finalise", "tf_sl_convolve", "tf_profile_enable", "tf_profile_reset", "tf_profile_read",
 )
+
+KERNEL_CLASSES = ("normalise", "pyramid", "polyexp", "flow_upsample", "fb_iter_coarse", "fb_iter_fullres",
+                  "sl_gather", "smooth_flow", "finalise")
 
 
 class FbParams(ctypes.Structure):
@@ -65,7 +68,9 @@ def load():
     lib.tf_flow_finalise.argtypes = [vp, vp, ci, ci, ci, cf, ci, ci, ci, vp]
     lib.tf_sl_convolve.argtypes = [vp, ci, ci, ci, vp, vp, vp, ll, ci, ci, ci, ci, ci, ci,
                                    ctypes.POINTER(ctypes.c_uint8), cd, vp]
-    for name in ("tf_fb_level_plan", "tf_fb_poly_constants", "tf_pair_normalise_u8", "tf_farneback_pairs",
+    lib.tf_profile_enable.argtypes = [ci]
+    lib.tf_profile_read.argtypes = [ci, ctypes.POINTER(cd), ctypes.POINTER(cd), ctypes.POINTER(ll)]
+    for name in ("tf_profile_enable", "tf_profile_reset", "tf_profile_read", "tf_fb_level_plan", "tf_fb_poly_constants", "tf_pair_normalise_u8", "tf_farneback_pairs",
                  "tf_smooth_flow_step", "tf_flow_finalise", "tf_sl_convolve"):
         getattr(lib, name).restype = ci
     if lib.tf_version() != 1:
@@ -112,3 +117,21 @@ def workspace_bytes(n_pairs, H, W, params=None):
 def structure_bytes(structure):
     s = np.ascontiguousarray(np.asarray(structure) != 0, dtype=np.uint8).reshape(27)
     return (ctypes.c_uint8 * 27)(*s.tolist())
+
+
+def profile_enable(on=True):
+    check(load().tf_profile_enable(int(bool(on))), "tf_profile_enable")
+
+
+def profile_reset():
+    check(load().tf_profile_reset(), "tf_profile_reset")
+
+
+def profile_read():
+    """{kernel class: dict(ms, bytes, launches)} accumulated since the last reset (synchronises)."""
+    out = {}
+    for i, name in enumerate(KERNEL_CLASSES):
+        ms, by, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        check(load().tf_profile_read(i, ctypes.byref(ms), ctypes.byref(by), ctypes.byref(n)), "tf_profile_read")
+        out[name] = dict(ms=ms.value, bytes=by.value, launches=n.value)
+    return out

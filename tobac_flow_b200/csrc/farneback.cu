@@ -177,10 +177,10 @@ extern "C" int tf_farneback_pairs(const uint8_t* q0, const uint8_t* q1, float* f
             const bool final_write = last_level && it == p->num_iters - 1;
             if (final_write) {
                 rc = launch_fb_iteration(ws.R, f_a, fwd, fwd_stride, bwd, bwd_stride, n_pairs, h, w, p->win_size,
-                                         p->max_value, s);
+                                         p->max_value, last_level, s);
             } else {
                 rc = launch_fb_iteration(ws.R, f_a, f_b, lvl_stride, f_b + (long long)h * w * 2, lvl_stride, n_pairs, h, w,
-                                         p->win_size, 0.f, s);
+                                         p->win_size, 0.f, last_level, s);
             }
             if (rc != TF_OK) return rc;
             float* t = f_a; f_a = f_b; f_b = t;

@@ -33,6 +33,6 @@ int launch_polyexp(const float* I, float* R, int n_img, int h, int w, const Poly
 //   out_fwd/out_bwd + p*stride: where direction 0 / 1 results go (h, w, 2)
 //   clamp > 0: clamp results to +-clamp
 int launch_fb_iteration(const float* R, const float* flow_in, float* out_fwd, long long fwd_stride, float* out_bwd,
-                        long long bwd_stride, int n_pairs, int h, int w, int win, float clamp, cudaStream_t s);
+                        long long bwd_stride, int n_pairs, int h, int w, int win, float clamp, bool full_res, cudaStream_t s);
 
 }  // namespace tf

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) fb_iter_kernel(const float* __restrict__ 
 }
 
 int launch_fb_iteration(const float* R, const float* flow_in, float* out_fwd, long long fwd_stride, float* out_bwd,
-                        long long bwd_stride, int n_pairs, int h, int w, int win, float clamp, cudaStream_t s) {
+                        long long bwd_stride, int n_pairs, int h, int w, int win, float clamp, bool full_res, cudaStream_t s) {
     if (win != 13) {
         set_error("fb iteration: only winSize 13 is built (got %d)", win);
         return TF_ERR_UNSUPPORTED;
@@ -198,6 +198,7 @@ int launch_fb_iteration(const float* R, const float* flow_in, float* out_fwd, lo
         attr_set = true;
     }
     const int nz_total = 2 * n_pairs;
+    LaunchTimer lt(full_res ? KC_FB_ITER_L0 : KC_FB_ITER, 56.0 * h * w * nz_total, s, cdiv(nz_total, 65534));
     for (int z0 = 0; z0 < nz_total; z0 += 65534) {
         const int nz = min(nz_total - z0, 65534);
         const int p0 = z0 / 2;

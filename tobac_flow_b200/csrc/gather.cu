@@ -278,9 +278,18 @@ __global__ void __launch_bounds__(256) sl_gather_kernel(GatherArgs a) {
     }
 }
 
+static thread_local double g_gather_bytes = 0;
+
 template <typename SrcT, typename ST, int INTERP, int RC>
 static int launch_gather(const GatherArgs& a, cudaStream_t s) {
     dim3 block(32, 8);
+    {
+        int n_out = 1;
+        if (RC == RC_NONE) { n_out = 0; for (int k = 0; k < 27; ++k) n_out += (a.structure >> k) & 1; }
+        const double per_px = 3.0 * sizeof(SrcT) + 16.0 + (double)n_out * sizeof(ST);
+        g_gather_bytes = per_px * a.H * a.W * a.n_frames;
+    }
+    LaunchTimer lt(KC_GATHER, g_gather_bytes, s, cdiv(a.n_frames, 65535));
     for (int t0 = 0; t0 < a.n_frames; t0 += 65535) {
         GatherArgs b = a;
         const int nt = min(a.n_frames - t0, 65535);
@@ -428,6 +437,7 @@ extern "C" int tf_smooth_flow_step(const float* fwd, const float* bwd, float* fw
     if (fwd == fwd_out || bwd == bwd_out) { set_error("tf_smooth_flow_step: outputs must not alias inputs"); return TF_ERR_INVALID_ARGUMENT; }
     cudaStream_t s = (cudaStream_t)stream;
     dim3 block(32, 8);
+    LaunchTimer lt(KC_SMOOTH, 32.0 * H * W * n_pairs, s, cdiv(n_pairs, 32767));
     for (int p0 = 0; p0 < n_pairs; p0 += 32767) {
         const int np = min(n_pairs - p0, 32767);
         dim3 grid(cdiv(W, 32), cdiv(H, 8), 2 * np);
@@ -449,6 +459,8 @@ extern "C" int tf_flow_finalise(float* fwd, float* bwd, int T, int H, int W, flo
     if (!fwd || !bwd || T < 0 || H <= 0 || W <= 0) { set_error("tf_flow_finalise: invalid argument"); return TF_ERR_INVALID_ARGUMENT; }
     const long long fe = (long long)H * W * 2;
     cudaStream_t s = (cudaStream_t)stream;
+    LaunchTimer lt(KC_FINALISE, (clamp_all && max_value > 0.f) ? 4.0 * fe * T * 4 : 4.0 * fe * 4, s,
+                   (clamp_all && max_value > 0.f) ? cdiv(T, 65535) : 2);
     if (clamp_all && max_value > 0.f) {
         for (int t0 = 0; t0 < T; t0 += 65535) {
             const int nt = min(T - t0, 65535);

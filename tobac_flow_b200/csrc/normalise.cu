@@ -146,6 +146,7 @@ extern "C" int tf_pair_normalise_u8(const float* f0, const float* f1, long long 
     const int vec_ok = (n % 4 == 0) && (frame_stride % 4 == 0) && (((uintptr_t)f0 | (uintptr_t)f1) % 16 == 0) &&
                        (((uintptr_t)q0 | (uintptr_t)q1) % 4 == 0);
     int* mm = reinterpret_cast<int*>(minmax_scratch);
+    LaunchTimer lt(KC_NORMALISE, 18.0 * n * n_pairs, s, 1 + 2 * cdiv(n_pairs, 65535));
     minmax_init_kernel<<<cdiv(n_pairs, 128), 128, 0, s>>>(mm, n_pairs);
     // enough blocks to fill 148 SMs x 8 resident blocks even for one pair; capped by the work available
     int bx = min(max(cdiv(n / 4, 256 * 4), 1), 1184);

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(256) polyexp_kernel(const float* __restrict__ 
 }
 
 int launch_polyexp(const float* I, float* R, int n_img, int h, int w, const PolyConsts& pc, cudaStream_t s) {
+    LaunchTimer lt(KC_POLYEXP, 24.0 * h * w * n_img, s, cdiv(n_img, 65535));
     for (int z0 = 0; z0 < n_img; z0 += 65535) {
         const int nz = min(n_img - z0, 65535);
         dim3 g(cdiv(w, PE_TW), cdiv(h, PE_TH), nz);

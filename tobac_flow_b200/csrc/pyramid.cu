@@ -138,6 +138,7 @@ int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int 
     const int rp = (h == H) ? 1 : 2;
     const double sx = (double)W / w, sy = (double)H / h;
     const int n_img = 2 * n_pairs;
+    LaunchTimer lt(KC_PYRAMID, (2.0 * H * W + 8.0 * h * w) * n_pairs, s, 2 * cdiv(n_img, 65534));
     for (int z0 = 0; z0 < n_img; z0 += 65534) {
         const int nz = min(n_img - z0, 65534);  // even, so image parity is preserved
         dim3 ga(cdiv(W, 256), h * rp, nz);
@@ -153,6 +154,7 @@ int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int 
 int launch_flow_upsample(const float* src, float* dst, int n_fields, int sh, int sw, int h, int w, float mul,
                          cudaStream_t s) {
     const double sx = sw > 0 ? (double)sw / w : 1.0, sy = sh > 0 ? (double)sh / h : 1.0;
+    LaunchTimer lt(KC_UPSAMPLE, (8.0 * h * w + 8.0 * sh * sw) * n_fields, s, cdiv(n_fields, 65535));
     for (int z0 = 0; z0 < n_fields; z0 += 65535) {
         const int nz = min(n_fields - z0, 65535);
         dim3 g(cdiv(w, 256), h, nz);

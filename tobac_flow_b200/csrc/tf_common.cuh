@@ -36,6 +36,26 @@ struct LevelPlan {
 
 LevelPlan make_level_plan(int H, int W, const tf_fb_params& p);
 
+// kernel classes for launch accounting (tf_profile_*)
+enum KClass {
+    KC_NORMALISE = 0, KC_PYRAMID, KC_POLYEXP, KC_UPSAMPLE, KC_FB_ITER, KC_FB_ITER_L0, KC_GATHER, KC_SMOOTH, KC_FINALISE,
+    KC_COUNT
+};
+
+// RAII launch record: counts launches / algorithmic bytes, and times the enclosed launches with CUDA events on `s`
+// when profiling is enabled.
+class LaunchTimer {
+public:
+    LaunchTimer(int klass, double bytes, cudaStream_t s, int n_launches = 1);
+    ~LaunchTimer();
+    LaunchTimer(const LaunchTimer&) = delete;
+    LaunchTimer& operator=(const LaunchTimer&) = delete;
+private:
+    int klass_;
+    cudaStream_t s_;
+    cudaEvent_t b_;
+};
+
 // streaming global loads/stores (data touched once per kernel: keep it out of L1)
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
