@@ -67,7 +67,7 @@ static Workspace carve(void* base, int n_pairs, int H, int W, const LevelPlan& l
         off += align_up(bytes, 256);
         return o;
     };
-    const size_t o_tmp = take(2 * P * tmp_px * 4), o_I = take(2 * P * N * 4), o_R = take(2 * P * 5 * N * 4);
+    const size_t o_tmp = take(2 * P * tmp_px * 4), o_I = take(2 * P * N * 4), o_R = take(2 * P * (size_t)r_img_stride(H, W) * 4);
     const size_t o_f0 = take(P * 2 * N * 8), o_f1 = take(P * 2 * N * 8), o_f2 = take(P * 2 * N * 8);
     Workspace ws{};
     char* b = reinterpret_cast<char*>(base);
@@ -164,7 +164,8 @@ extern "C" int tf_farneback_pairs(const uint8_t* q0, const uint8_t* q1, float* f
         // level images + polynomial expansion for the 2*n_pairs images
         rc = launch_pyramid_level(q0, q1, n_pairs, H, W, h, w, lp.ksize[li], lp.sigma[li], ws.tmp, ws.I, s);
         if (rc != TF_OK) return rc;
-        rc = launch_polyexp(ws.I, ws.R, 2 * n_pairs, h, w, pc, s);
+        const long long rs = r_img_stride(h, w);
+        rc = launch_polyexp(ws.I, ws.R, rs, 2 * n_pairs, h, w, pc, s);
         if (rc != TF_OK) return rc;
         // initial flow: zeros at the coarsest level, else resize(prev) * (1 / pyr_scale)
         float* f_in = ws.flow[cur];
@@ -176,10 +177,10 @@ extern "C" int tf_farneback_pairs(const uint8_t* q0, const uint8_t* q1, float* f
         for (int it = 0; it < p->num_iters; ++it) {
             const bool final_write = last_level && it == p->num_iters - 1;
             if (final_write) {
-                rc = launch_fb_iteration(ws.R, f_a, fwd, fwd_stride, bwd, bwd_stride, n_pairs, h, w, p->win_size,
+                rc = launch_fb_iteration(ws.R, rs, f_a, fwd, fwd_stride, bwd, bwd_stride, n_pairs, h, w, p->win_size,
                                          p->max_value, last_level, s);
             } else {
-                rc = launch_fb_iteration(ws.R, f_a, f_b, lvl_stride, f_b + (long long)h * w * 2, lvl_stride, n_pairs, h, w,
+                rc = launch_fb_iteration(ws.R, rs, f_a, f_b, lvl_stride, f_b + (long long)h * w * 2, lvl_stride, n_pairs, h, w,
                                          p->win_size, 0.f, last_level, s);
             }
             if (rc != TF_OK) return rc;

@@ -24,15 +24,17 @@ int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int 
 int launch_flow_upsample(const float* src, float* dst, int n_fields, int sh, int sw, int h, int w, float mul,
                          cudaStream_t s);
 
-// R (n_img, 5, h, w) planes from I (n_img, h, w)
-int launch_polyexp(const float* I, float* R, int n_img, int h, int w, const PolyConsts& pc, cudaStream_t s);
+// R: per image `img_stride` floats (a multiple of 4): a float4 plane (c0..c3) of h*w texels, then a float plane (c4)
+inline long long r_img_stride(int h, int w) { return ((long long)5 * h * w + 3) / 4 * 4; }
+int launch_polyexp(const float* I, float* R, long long img_stride, int n_img, int h, int w, const PolyConsts& pc,
+                   cudaStream_t s);
 
 // One Jacobi iteration (UpdateMatrices + 13x13 box + 2x2 solve) for n_pairs x 2 directions.
-//   R          (2*n_pairs, 5, h, w): image 2p = prev, 2p+1 = next
+//   R          2*n_pairs images in the layout above: image 2p = prev, 2p+1 = next
 //   flow_in    (n_pairs, 2, h, w, 2)   [pair][direction]
 //   out_fwd/out_bwd + p*stride: where direction 0 / 1 results go (h, w, 2)
 //   clamp > 0: clamp results to +-clamp
-int launch_fb_iteration(const float* R, const float* flow_in, float* out_fwd, long long fwd_stride, float* out_bwd,
+int launch_fb_iteration(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride, float* out_bwd,
                         long long bwd_stride, int n_pairs, int h, int w, int win, float clamp, bool full_res, cudaStream_t s);
 
 }  // namespace tf

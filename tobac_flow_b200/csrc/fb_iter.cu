@@ -1,23 +1,37 @@
 // K4+K5: one fused Farneback iteration = FarnebackUpdateMatrices + FarnebackUpdateFlow_Blur (box window).
 //
 // OpenCV's sweep is a pure Jacobi update (the matrices it refreshes behind the sliding window are never re-read in the
-// same sweep), so flow buffers ping-pong and M is never materialised in HBM:
-//   phase 1  M(y, x) for the output tile + 6-px halo (replicate-clamped coordinates): flow, R0, bilinear R1 at p+flow
-//   phase 2  vertical 13-sums, sliding, in place in shared memory (one thread per column-channel)
-//   phase 3  horizontal 13-sums (sliding over 8 outputs per thread), 2x2 solve in registers, float2 store
+// same sweep), so flow buffers ping-pong and M is never materialised in HBM.
+//
+// Strip-marching design (the shape of OpenCV's own sliding window, mapped to a CTA):
+//   * a CTA owns a strip of NT columns (NT - 12 outputs + a 6-column halo on each side) and marches down a chunk of
+//     rows; there is no row halo re-read apart from a 12-row warm-up per chunk;
+//   * M phase, one thread per column, software-pipelined one row ahead (the next row's gathers and the flow of the
+//     row after that are in flight while the current row is computed): flow (8 B), R0 (float4 + float) and the
+//     bilinear R1 gather at p + flow (4 x (float4 + float)) -> the five M terms.  Rows are handled in batches of 4;
+//     the vertical 13-row window sum is assembled from fresh partial sums (suffix of batch b-3 kept in a small
+//     shared-memory ring, the full sums of batches b-2 and b-1 in registers, the running prefix of batch b), so
+//     rounding never accumulates down the chunk;
+//   * H phase, every 4 rows: the vertical sums of 4 rows are exchanged through shared memory; each thread takes one row
+//     and 4 adjacent outputs, slides the horizontal 13-column window over them, solves the 2x2 systems in registers and
+//     stores the new flow (32 B per thread, coalesced).
+//   * forward and backward CTAs of the same pair and strip are adjacent in launch order, so the second reader of the
+//     shared R planes hits L2.
 // Algorithmic HBM bytes per pixel-iteration: flow 8 + R0 20 + R1 20 read, flow 8 written = 56 B.
 #include "farneback_internal.cuh"
 
 namespace tf {
 
-constexpr int IT_TW = 64, IT_TH = 32;
+constexpr int IT_HALO = 6, IT_WIN = 13, IT_RB = 4;
 
-template <int HALO>
-struct IterCfg {
-    static constexpr int RW = IT_TW + 2 * HALO;   // region width  (76)
-    static constexpr int RH = IT_TH + 2 * HALO;   // region height (44)
-    static constexpr int PITCH = (RW + 3) / 4 * 4;
-    static constexpr int SMEM_BYTES = 5 * RH * PITCH * (int)sizeof(float);
+template <int NT>
+struct StripCfg {
+    static constexpr int OUT_W = NT - 2 * IT_HALO;
+    static constexpr int VPAD = 8;
+    static constexpr int VP = NT + 2 * VPAD;                 // pitch of a row of vertical sums (zero pads both sides)
+    static constexpr int RING_FLOATS = 3 * 3 * 5 * NT;       // 3 batches x suffix sums X1..X3 x 5 channels
+    static constexpr int VBUF_FLOATS = 2 * IT_RB * 5 * VP;   // double-buffered
+    static constexpr int SMEM_BYTES = (RING_FLOATS + VBUF_FLOATS) * (int)sizeof(float);
 };
 
 __device__ __forceinline__ float border_factor(int p, int n) {
@@ -29,43 +43,72 @@ __device__ __forceinline__ float border_factor(int p, int n) {
     return s;
 }
 
-// FarnebackUpdateMatrices for one pixel.  R planes: R[c * plane + y * w + x]
-__device__ __forceinline__ void update_matrix_px(const float* __restrict__ R0, const float* __restrict__ R1,
-                                                 long long plane, int w, int h, int x, int y, float dx, float dy,
-                                                 float m[5]) {
-    const long long o = (long long)y * w + x;
-    float fx = (float)x + dx, fy = (float)y + dy;
+// Everything one pixel's FarnebackUpdateMatrices reads: R0 at the pixel, the four bilinear taps of R1 at p + flow.
+struct Taps {
+    float4 c;  float c4;                 // R0: (c0..c3), c4
+    float4 p00, p01, p10, p11;           // R1 float4 plane taps
+    float q00, q01, q10, q11;            // R1 c4 plane taps
+    float fx, fy, dx, dy;                // bilinear fractions and the flow
+    int y;                               // image row (replicate-clamped)
+    bool inside;
+};
+
+struct RPlanes {
+    const float4* R0a; const float* R0b; const float4* R1a; const float* R1b;
+};
+
+// issue the loads of one pixel (addresses are always valid; `inside` says whether the R1 taps are used)
+__device__ __forceinline__ void issue_taps(Taps& t, const RPlanes& R, int w, int h, int x, int y, float2 f) {
+    const int o = y * w + x;
+    t.y = y;
+    t.dx = f.x;
+    t.dy = f.y;
+    float fx = (float)x + f.x, fy = (float)y + f.y;
     const float flx = floorf(fx), fly = floorf(fy);
     const int x1 = (int)flx, y1 = (int)fly;
-    fx -= flx;
-    fy -= fly;
+    t.fx = fx - flx;
+    t.fy = fy - fly;
+    t.inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+    const int o1 = t.inside ? y1 * w + x1 : 0;
+    const int dx1 = t.inside ? 1 : 0, dy1 = t.inside ? w : 0;
+    t.c = __ldg(R.R0a + o);
+    t.c4 = __ldg(R.R0b + o);
+    t.p00 = __ldg(R.R1a + o1);
+    t.p01 = __ldg(R.R1a + o1 + dx1);
+    t.p10 = __ldg(R.R1a + o1 + dy1);
+    t.p11 = __ldg(R.R1a + o1 + dy1 + dx1);
+    t.q00 = __ldg(R.R1b + o1);
+    t.q01 = __ldg(R.R1b + o1 + dx1);
+    t.q10 = __ldg(R.R1b + o1 + dy1);
+    t.q11 = __ldg(R.R1b + o1 + dy1 + dx1);
+}
+
+// FarnebackUpdateMatrices for one pixel from its loaded taps
+__device__ __forceinline__ void matrix_from_taps(const Taps& t, int h, float sc_x, float m[5]) {
     float r2, r3, r4, r5, r6;
-    const float c2 = R0[2 * plane + o], c3 = R0[3 * plane + o], c4 = R0[4 * plane + o];
-    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+    if (t.inside) {
+        const float fx = t.fx, fy = t.fy;
         const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        const float* p = R1 + (long long)y1 * w + x1;
-#define TF_BILIN(c) (a00 * p[(c) * plane] + a01 * p[(c) * plane + 1] + a10 * p[(c) * plane + w] + a11 * p[(c) * plane + w + 1])
-        r2 = TF_BILIN(0);
-        r3 = TF_BILIN(1);
-        r4 = TF_BILIN(2);
-        r5 = TF_BILIN(3);
-        r6 = TF_BILIN(4);
-#undef TF_BILIN
-        r4 = (c2 + r4) * 0.5f;
-        r5 = (c3 + r5) * 0.5f;
-        r6 = (c4 + r6) * 0.25f;
+        r2 = a00 * t.p00.x + a01 * t.p01.x + a10 * t.p10.x + a11 * t.p11.x;
+        r3 = a00 * t.p00.y + a01 * t.p01.y + a10 * t.p10.y + a11 * t.p11.y;
+        r4 = a00 * t.p00.z + a01 * t.p01.z + a10 * t.p10.z + a11 * t.p11.z;
+        r5 = a00 * t.p00.w + a01 * t.p01.w + a10 * t.p10.w + a11 * t.p11.w;
+        r6 = a00 * t.q00 + a01 * t.q01 + a10 * t.q10 + a11 * t.q11;
+        r4 = (t.c.z + r4) * 0.5f;
+        r5 = (t.c.w + r5) * 0.5f;
+        r6 = (t.c4 + r6) * 0.25f;
     } else {
         r2 = r3 = 0.f;
-        r4 = c2;
-        r5 = c3;
-        r6 = c4 * 0.5f;
+        r4 = t.c.z;
+        r5 = t.c.w;
+        r6 = t.c4 * 0.5f;
     }
-    r2 = (R0[o] - r2) * 0.5f;
-    r3 = (R0[plane + o] - r3) * 0.5f;
-    r2 += r4 * dy + r6 * dx;
-    r3 += r6 * dy + r5 * dx;
-    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
-        const float sc = border_factor(x, w) * border_factor(y, h);
+    r2 = (t.c.x - r2) * 0.5f;
+    r3 = (t.c.y - r3) * 0.5f;
+    r2 += r4 * t.dy + r6 * t.dx;
+    r3 += r6 * t.dy + r5 * t.dx;
+    if (sc_x != 1.f || (unsigned)(t.y - 5) >= (unsigned)(h - 10)) {
+        const float sc = sc_x * border_factor(t.y, h);
         r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
     }
     m[0] = r4 * r4 + r6 * r6;
@@ -83,130 +126,192 @@ __device__ __forceinline__ float diff_of_products(float a, float b, float c, flo
     return dop + err;
 }
 
-template <int HALO>
-__global__ void __launch_bounds__(256) fb_iter_kernel(const float* __restrict__ R, const float* __restrict__ flow_in,
-                                                      float* __restrict__ out_fwd, long long fwd_stride,
-                                                      float* __restrict__ out_bwd, long long bwd_stride, int h, int w,
-                                                      float clampv) {
-    using C = IterCfg<HALO>;
-    constexpr int WIN = 2 * HALO + 1;
+template <int NT>
+__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 4))
+fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const float* __restrict__ flow_in,
+                     float* __restrict__ out_fwd, long long fwd_stride, float* __restrict__ out_bwd,
+                     long long bwd_stride, int h, int w, int chunk_rows, float clampv) {
+    using C = StripCfg<NT>;
     extern __shared__ __align__(16) float smem[];
-    // layout: s[c][r][col], pitch C::PITCH
-    const int pd = blockIdx.z;  // 2*pair + direction
-    const int pair = pd >> 1, dir = pd & 1;
-    const long long plane = (long long)h * w;
-    const float* Rp = R + (long long)(2 * pair) * 5 * plane;
-    const float* Rn = Rp + 5 * plane;
+    float* ring = smem;                       // [batch % 3][X1..X3][k][col]
+    float* vbuf = smem + C::RING_FLOATS;      // [buf][row][k][VP]
+    const int tid = threadIdx.x;
+    const int strip = blockIdx.x >> 1, dir = blockIdx.x & 1;
+    const int pair = blockIdx.z;
+    const int plane = h * w;
+    const float* Rp = R + (long long)(2 * pair) * img_stride;
+    const float* Rn = Rp + img_stride;
     const float* R0 = dir ? Rn : Rp;
     const float* R1 = dir ? Rp : Rn;
-    const float2* fin = reinterpret_cast<const float2*>(flow_in) + (long long)pd * plane;
+    RPlanes RP;
+    RP.R0a = reinterpret_cast<const float4*>(R0);
+    RP.R0b = R0 + 4 * (long long)plane;
+    RP.R1a = reinterpret_cast<const float4*>(R1);
+    RP.R1b = R1 + 4 * (long long)plane;
+    const float2* fin = reinterpret_cast<const float2*>(flow_in) + (long long)(2 * pair + dir) * plane;
     float2* fout = reinterpret_cast<float2*>(dir ? out_bwd + (long long)pair * bwd_stride
                                                  : out_fwd + (long long)pair * fwd_stride);
-    const int x0 = blockIdx.x * IT_TW, y0 = blockIdx.y * IT_TH;
-    const int tid = threadIdx.x;
-    constexpr int CH = C::RH * C::PITCH;
+    const int x0 = strip * C::OUT_W;
+    const int yc0 = blockIdx.y * chunk_rows;
+    const int yc1 = min(yc0 + chunk_rows, h);
 
-    // phase 1: M over the halo region (coordinates clamped = replicate border of the box filter)
-    for (int idx = tid; idx < C::RH * C::RW; idx += 256) {
-        const int r = idx / C::RW, c = idx - r * C::RW;
-        const int gy = min(max(y0 + r - HALO, 0), h - 1);
-        const int gx = min(max(x0 + c - HALO, 0), w - 1);
-        const float2 f = fin[(long long)gy * w + gx];
-        float m[5];
-        update_matrix_px(R0, R1, plane, w, h, gx, gy, f.x, f.y, m);
-        const int so = r * C::PITCH + c;
+    // M-phase identity: one column of the strip (replicate-clamped = the box filter's border rule)
+    const int gx = min(max(x0 - IT_HALO + tid, 0), w - 1);
+    const float sc_x = border_factor(gx, w);
+    // H-phase identity: one row of the batch, 4 adjacent output columns
+    const int hr = tid / (NT / 4), cg = tid % (NT / 4);
+
+    // zero the suffix-sum ring column and the pads of the vertical-sum rows
 #pragma unroll
-        for (int k = 0; k < 5; ++k) smem[k * CH + so] = m[k];
+    for (int s = 0; s < 3 * 3 * 5; ++s) ring[s * NT + tid] = 0.f;
+    for (int i = tid; i < 2 * IT_RB * 5 * 2 * C::VPAD; i += NT) {
+        const int rowk = i / (2 * C::VPAD), j = i % (2 * C::VPAD);
+        vbuf[rowk * C::VP + (j < C::VPAD ? j : NT + j)] = 0.f;
     }
+    // the 13-row window of row r0+j is: suffix X_j of batch b-3 (4-j rows) + batches b-2, b-1 + prefix P_j of batch b.
+    // Every partial sum is formed fresh from at most 4 values, so rounding never accumulates down the chunk.
+    float B1[5], B2[5], B3[5];   // full sums of batches b-1, b-2, b-3
+#pragma unroll
+    for (int k = 0; k < 5; ++k) B1[k] = B2[k] = B3[k] = 0.f;
+    const int r_begin = yc0 - IT_HALO;
+    const int n_rows = (yc1 - yc0) + 2 * IT_HALO;
+    const int n_batches = (n_rows + IT_RB - 1) / IT_RB;
+    int rb = 0;                  // ring slot of batch b (b % 3): overwritten at the end of the batch, read as b-3 first
+
+    // software pipeline: taps of the current row are in registers / in flight, the next row's flow is in flight
+    auto row_y = [&](int i) { return min(max(r_begin + i, 0), h - 1); };
+    Taps cur;
+    issue_taps(cur, RP, w, h, gx, row_y(0), __ldg(fin + row_y(0) * w + gx));
+    float2 f_next = __ldg(fin + row_y(1) * w + gx);
     __syncthreads();
 
-    // phase 2: vertical window sums, in place: V[r] = sum_{j<WIN} M[r + j], r in [0, TH)
-    for (int task = tid; task < 5 * C::RW; task += 256) {
-        const int k = task / C::RW, c = task - k * C::RW;
-        float* col = smem + k * CH + c;
-        float acc = 0.f;
+    for (int b = 0; b < n_batches; ++b) {
+        float* vb = vbuf + (b & 1) * (IT_RB * 5 * C::VP);
+        float* rg = ring + rb * (3 * 5 * NT) + tid;
+        float P[IT_RB][5];
+        // ---- M phase: 4 rows of this thread's column -------------------------------------------------------------
 #pragma unroll
-        for (int j = 0; j < WIN; ++j) acc += col[j * C::PITCH];
-        float oldest = col[0];
-        col[0] = acc;
-        for (int r = 1; r < IT_TH; ++r) {
-            const float incoming = col[(r + WIN - 1) * C::PITCH];
-            acc += incoming - oldest;
-            oldest = col[r * C::PITCH];
-            col[r * C::PITCH] = acc;
+        for (int j = 0; j < IT_RB; ++j) {
+            const int i = b * IT_RB + j;
+            // prefetch: the next row's taps (its flow has arrived by now) and the flow of the row after that
+            Taps nxt;
+            issue_taps(nxt, RP, w, h, gx, row_y(i + 1), f_next);
+            f_next = __ldg(fin + row_y(i + 2) * w + gx);
+            float m[5];
+            matrix_from_taps(cur, h, sc_x, m);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                P[j][k] = (j == 0) ? m[k] : P[j - 1][k] + m[k];
+                const float xold = (j == 0) ? B3[k] : rg[((j - 1) * 5 + k) * NT];   // suffix X_j of batch b-3
+                vb[(j * 5 + k) * C::VP + C::VPAD + tid] = (xold + B2[k]) + (B1[k] + P[j][k]);
+            }
+            cur = nxt;
         }
-    }
-    __syncthreads();
-
-    // phase 3: horizontal window sums for 8 consecutive outputs, solve, store
-    {
-        const int r = tid >> 3, seg = tid & 7;
-        const int gy = y0 + r;
-        const int cx = seg * 8;  // first output column within the tile
-        float g[5][8];
+        // publish this batch's suffix sums X1..X3 (X_j = rows j..3 = P3 - P_{j-1}) and rotate the batch sums
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            const float* row = smem + k * CH + r * C::PITCH + cx;
-            float v[8 + 2 * HALO];
 #pragma unroll
-            for (int j = 0; j < (8 + 2 * HALO) / 4; ++j) {
-                const float4 t = *reinterpret_cast<const float4*>(row + 4 * j);
-                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-            }
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < WIN; ++j) acc += v[j];
-            g[k][0] = acc;
-#pragma unroll
-            for (int i = 1; i < 8; ++i) {
-                acc += v[i + WIN - 1] - v[i - 1];
-                g[k][i] = acc;
-            }
+            for (int j = 1; j < IT_RB; ++j) rg[((j - 1) * 5 + k) * NT] = P[IT_RB - 1][k] - P[j - 1][k];
+            B3[k] = B2[k];
+            B2[k] = B1[k];
+            B1[k] = P[IT_RB - 1][k];
         }
-        if (gy < h) {
-            const float scale = 1.f / (float)(WIN * WIN);
+        rb = (rb == 2) ? 0 : rb + 1;
+        __syncthreads();
+        // ---- H phase: row hr of the batch, outputs 4*cg .. 4*cg+3 ------------------------------------------------
+        const int y = r_begin + b * IT_RB + hr - IT_HALO;
+        if (y >= yc0 && y < yc1) {
+            float g[5][4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int gx = x0 + cx + i;
-                if (gx < w) {
-                    const float g11 = g[0][i] * scale, g12 = g[1][i] * scale, g22 = g[2][i] * scale;
-                    const float h1 = g[3][i] * scale, h2 = g[4][i] * scale;
-                    const float idet = 1.f / (diff_of_products(g11, g22, g12, g12) + 1e-3f);
-                    float fx = diff_of_products(g11, h2, g12, h1) * idet;
-                    float fy = diff_of_products(g22, h1, g12, h2) * idet;
-                    if (clampv > 0.f) {
-                        fx = fminf(fmaxf(fx, -clampv), clampv);
-                        fy = fminf(fmaxf(fy, -clampv), clampv);
-                    }
-                    fout[(long long)gy * w + gx] = make_float2(fx, fy);
+            for (int k = 0; k < 5; ++k) {
+                // v[j] = vertical sum at region column 4*cg - 8 + j
+                const float4* row = reinterpret_cast<const float4*>(vb + (hr * 5 + k) * C::VP + 4 * cg);
+                float v[20];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const float4 t = row[q];
+                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
                 }
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 2; j < 2 + IT_WIN; ++j) acc += v[j];
+                g[k][0] = acc;
+#pragma unroll
+                for (int i = 1; i < 4; ++i) {
+                    acc += v[i + 1 + IT_WIN] - v[i + 1];
+                    g[k][i] = acc;
+                }
+            }
+            const float scale = 1.f / (float)(IT_WIN * IT_WIN);
+            float2 o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float g11 = g[0][i] * scale, g12 = g[1][i] * scale, g22 = g[2][i] * scale;
+                const float h1 = g[3][i] * scale, h2 = g[4][i] * scale;
+                const float idet = 1.f / (diff_of_products(g11, g22, g12, g12) + 1e-3f);
+                float fx = diff_of_products(g11, h2, g12, h1) * idet;
+                float fy = diff_of_products(g22, h1, g12, h2) * idet;
+                if (clampv > 0.f) {
+                    fx = fminf(fmaxf(fx, -clampv), clampv);
+                    fy = fminf(fmaxf(fy, -clampv), clampv);
+                }
+                o[i] = make_float2(fx, fy);
+            }
+            const int c0 = 4 * cg;                         // region column of o[0]
+            const int xg = x0 - IT_HALO + c0;              // image column of o[0]
+            float2* dst = fout + (long long)y * w + xg;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = c0 + i;
+                if (c >= IT_HALO && c < NT - IT_HALO && xg + i < w) dst[i] = o[i];
             }
         }
     }
 }
 
-int launch_fb_iteration(const float* R, const float* flow_in, float* out_fwd, long long fwd_stride, float* out_bwd,
-                        long long bwd_stride, int n_pairs, int h, int w, int win, float clamp, bool full_res, cudaStream_t s) {
-    if (win != 13) {
+template <int NT>
+static void launch_strip(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride,
+                         float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, float clamp, cudaStream_t s) {
+    using C = StripCfg<NT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(fb_iter_strip_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        attr_set = true;
+    }
+    const int strips = cdiv(w, C::OUT_W);
+    // rows per chunk: enough CTAs for ~2 waves of 148 SMs x resident CTAs, but chunks no shorter than 48 rows
+    // (12 warm-up rows per chunk) and no longer than 256
+    const int resident = 148 * (NT == 256 ? 2 : 4);
+    int chunks = cdiv(2 * resident, max(1, 2 * strips * n_pairs));
+    chunks = max(1, min(chunks, cdiv(h, 48)));
+    chunks = max(chunks, cdiv(h, 256));
+    const int chunk_rows = cdiv(h, chunks);
+    chunks = cdiv(h, chunk_rows);
+    for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
+        const int np = min(n_pairs - p0, 65535);
+        dim3 g(2 * strips, chunks, np);
+        fb_iter_strip_kernel<NT><<<g, NT, C::SMEM_BYTES, s>>>(R + (long long)(2 * p0) * img_stride, img_stride,
+                                                              flow_in + (long long)(2 * p0) * 2 * h * w,
+                                                              out_fwd + p0 * fwd_stride, fwd_stride,
+                                                              out_bwd + p0 * bwd_stride, bwd_stride, h, w, chunk_rows, clamp);
+    }
+}
+
+int launch_fb_iteration(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride,
+                        float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, int win, float clamp,
+                        bool full_res, cudaStream_t s) {
+    if (win != IT_WIN) {
         set_error("fb iteration: only winSize 13 is built (got %d)", win);
         return TF_ERR_UNSUPPORTED;
     }
-    using C = IterCfg<6>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(fb_iter_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        attr_set = true;
-    }
-    const int nz_total = 2 * n_pairs;
-    LaunchTimer lt(full_res ? KC_FB_ITER_L0 : KC_FB_ITER, 56.0 * h * w * nz_total, s, cdiv(nz_total, 65534));
-    for (int z0 = 0; z0 < nz_total; z0 += 65534) {
-        const int nz = min(nz_total - z0, 65534);
-        const int p0 = z0 / 2;
-        dim3 g(cdiv(w, IT_TW), cdiv(h, IT_TH), nz);
-        fb_iter_kernel<6><<<g, 256, C::SMEM_BYTES, s>>>(R + (long long)z0 * 5 * h * w, flow_in + (long long)z0 * 2 * h * w,
-                                                        out_fwd + p0 * fwd_stride, fwd_stride, out_bwd + p0 * bwd_stride,
-                                                        bwd_stride, h, w, clamp);
-    }
+    if ((long long)h * w > 0x3fffffffLL) { set_error("fb iteration: level too large"); return TF_ERR_INVALID_ARGUMENT; }
+    LaunchTimer lt(full_res ? KC_FB_ITER_L0 : KC_FB_ITER, 56.0 * h * w * 2 * n_pairs, s, cdiv(n_pairs, 65535));
+    // strip width: the configuration that wastes fewer columns
+    const int pad256 = cdiv(w, StripCfg<256>::OUT_W) * 256, pad128 = cdiv(w, StripCfg<128>::OUT_W) * 128;
+    if (pad256 <= pad128)
+        launch_strip<256>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
+    else
+        launch_strip<128>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
     return check_launch("fb iteration");
 }
 

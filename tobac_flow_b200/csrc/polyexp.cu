@@ -1,6 +1,6 @@
 // K3: Farneback polynomial expansion (OpenCV FarnebackPolyExp, polyN = 5): separable 11-tap tile convolution with
-// replicate borders.  Input level image I (h, w) fp32 -> five coefficient planes R[c] (h, w) fp32 (SoA so that the
-// iteration kernel's bilinear gathers are coalesced per plane).
+// replicate borders.  Input level image I (h, w) fp32 -> per image a float4 plane (c0..c3) followed by a float plane
+// (c4), so the iteration kernel's bilinear gathers are one 16-byte and one 4-byte coalesced load per tap.
 // Shared-memory tile with a 5-pixel halo: vertical pass to three moment arrays, horizontal pass to six sums.
 // HBM traffic: 4 B/px read (+ halo re-reads that hit L2) and 20 B/px written.
 #include "farneback_internal.cuh"
@@ -12,8 +12,8 @@ constexpr int PE_SW = PE_TW + 2 * PE_N;      // 74 columns incl. halo
 constexpr int PE_SWP = PE_SW + 2;            // padded row pitch (76)
 constexpr int PE_SH = PE_TH + 2 * PE_N;      // 42 rows incl. halo
 
-__global__ void __launch_bounds__(256) polyexp_kernel(const float* __restrict__ I, float* __restrict__ R, int h, int w,
-                                                      PolyConsts pc) {
+__global__ void __launch_bounds__(256) polyexp_kernel(const float* __restrict__ I, float* __restrict__ R,
+                                                      long long img_stride, int h, int w, PolyConsts pc) {
     __shared__ float s_in[PE_SH][PE_SWP];
     __shared__ float s_v[3][PE_TH][PE_SWP];
     const int img = blockIdx.z;
@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(256) polyexp_kernel(const float* __restrict__ 
     const int c = tid & (PE_TW - 1);
     const int gx = x0 + c;
     const long long plane = (long long)h * w;
-    float* dst = R + (long long)img * 5 * plane;
+    float4* dst_a = reinterpret_cast<float4*>(R + (long long)img * img_stride);
+    float* dst_b = R + (long long)img * img_stride + 4 * plane;
     for (int r = tid >> 6; r < PE_TH; r += 4) {
         const int gy = y0 + r;
         if (gx >= w || gy >= h) continue;
@@ -72,20 +73,18 @@ __global__ void __launch_bounds__(256) polyexp_kernel(const float* __restrict__ 
             b5 += (v2[k] + v2[-k]) * pc.g[k];
         }
         const long long o = (long long)gy * w + gx;
-        dst[o] = b3 * pc.ig11;
-        dst[plane + o] = b2 * pc.ig11;
-        dst[2 * plane + o] = b1 * pc.ig03 + b5 * pc.ig33;
-        dst[3 * plane + o] = b1 * pc.ig03 + b4 * pc.ig33;
-        dst[4 * plane + o] = b6 * pc.ig55;
+        dst_a[o] = make_float4(b3 * pc.ig11, b2 * pc.ig11, b1 * pc.ig03 + b5 * pc.ig33, b1 * pc.ig03 + b4 * pc.ig33);
+        dst_b[o] = b6 * pc.ig55;
     }
 }
 
-int launch_polyexp(const float* I, float* R, int n_img, int h, int w, const PolyConsts& pc, cudaStream_t s) {
+int launch_polyexp(const float* I, float* R, long long img_stride, int n_img, int h, int w, const PolyConsts& pc,
+                   cudaStream_t s) {
     LaunchTimer lt(KC_POLYEXP, 24.0 * h * w * n_img, s, cdiv(n_img, 65535));
     for (int z0 = 0; z0 < n_img; z0 += 65535) {
         const int nz = min(n_img - z0, 65535);
         dim3 g(cdiv(w, PE_TW), cdiv(h, PE_TH), nz);
-        polyexp_kernel<<<g, 256, 0, s>>>(I + (long long)z0 * h * w, R + (long long)z0 * 5 * h * w, h, w, pc);
+        polyexp_kernel<<<g, 256, 0, s>>>(I + (long long)z0 * h * w, R + (long long)z0 * img_stride, img_stride, h, w, pc);
     }
     return check_launch("polyexp");
 }
