@@ -178,11 +178,13 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
     const int n_batches = (n_rows + IT_RB - 1) / IT_RB;
     int rb = 0;                  // ring slot of batch b (b % 3): overwritten at the end of the batch, read as b-3 first
 
-    // software pipeline: taps of the current row are in registers / in flight, the next row's flow is in flight
+    // software pipeline: the current row's taps are in registers, the next row's taps and four rows of flow in flight
     auto row_y = [&](int i) { return min(max(r_begin + i, 0), h - 1); };
     Taps cur;
     issue_taps(cur, RP, w, h, gx, row_y(0), __ldg(fin + row_y(0) * w + gx));
-    float2 f_next = __ldg(fin + row_y(1) * w + gx);
+    float2 fq[IT_RB];            // flows of rows i+1 .. i+4 (a DRAM round trip ahead of their use)
+#pragma unroll
+    for (int j = 0; j < IT_RB; ++j) fq[j] = __ldg(fin + row_y(1 + j) * w + gx);
     __syncthreads();
 
     for (int b = 0; b < n_batches; ++b) {
@@ -193,10 +195,10 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
 #pragma unroll
         for (int j = 0; j < IT_RB; ++j) {
             const int i = b * IT_RB + j;
-            // prefetch: the next row's taps (its flow has arrived by now) and the flow of the row after that
+            // prefetch: the next row's taps (its flow was requested four rows ago) and the flow of row i+5
             Taps nxt;
-            issue_taps(nxt, RP, w, h, gx, row_y(i + 1), f_next);
-            f_next = __ldg(fin + row_y(i + 2) * w + gx);
+            issue_taps(nxt, RP, w, h, gx, row_y(i + 1), fq[j]);
+            fq[j] = __ldg(fin + row_y(i + 1 + IT_RB) * w + gx);
             float m[5];
             matrix_from_taps(cur, h, sc_x, m);
 #pragma unroll
