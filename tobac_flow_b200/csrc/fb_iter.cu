@@ -23,13 +23,16 @@
 namespace tf {
 
 constexpr int IT_HALO = 6, IT_WIN = 13, IT_RB = 4;
+constexpr int IT_PREFETCH_ROWS = 6;
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int NT>
 struct StripCfg {
     static constexpr int OUT_W = NT - 2 * IT_HALO;
     static constexpr int VPAD = 8;
     static constexpr int VP = NT + 2 * VPAD;                 // pitch of a row of vertical sums (zero pads both sides)
-    static constexpr int RING_FLOATS = 3 * 3 * 5 * NT;       // 3 batches x suffix sums X1..X3 x 5 channels
+    static constexpr int RING_FLOATS = 3 * 3 * 5 * NT;       // 3 batches x prefix sums P0..P2 x 5 channels
     static constexpr int VBUF_FLOATS = 2 * IT_RB * 5 * VP;   // double-buffered
     static constexpr int SMEM_BYTES = (RING_FLOATS + VBUF_FLOATS) * (int)sizeof(float);
 };
@@ -69,18 +72,23 @@ __device__ __forceinline__ void issue_taps(Taps& t, const RPlanes& R, int w, int
     t.fx = fx - flx;
     t.fy = fy - fly;
     t.inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
-    const int o1 = t.inside ? y1 * w + x1 : 0;
-    const int dx1 = t.inside ? 1 : 0, dy1 = t.inside ? w : 0;
+    // out-of-image positions read a clamped (valid) 2x2 footprint whose values are then ignored; levels are never
+    // narrower than 2 px in practice, and max(.., 0) keeps the address valid even then
+    const int xc = max(min(x1, w - 2), 0), yc = max(min(y1, h - 2), 0);
+    const float4* a0 = R.R1a + (yc * w + xc);
+    const float4* a1 = a0 + w;
+    const float* b0 = R.R1b + (yc * w + xc);
+    const float* b1 = b0 + w;
     t.c = __ldg(R.R0a + o);
     t.c4 = __ldg(R.R0b + o);
-    t.p00 = __ldg(R.R1a + o1);
-    t.p01 = __ldg(R.R1a + o1 + dx1);
-    t.p10 = __ldg(R.R1a + o1 + dy1);
-    t.p11 = __ldg(R.R1a + o1 + dy1 + dx1);
-    t.q00 = __ldg(R.R1b + o1);
-    t.q01 = __ldg(R.R1b + o1 + dx1);
-    t.q10 = __ldg(R.R1b + o1 + dy1);
-    t.q11 = __ldg(R.R1b + o1 + dy1 + dx1);
+    t.p00 = __ldg(a0);
+    t.p01 = __ldg(a0 + 1);
+    t.p10 = __ldg(a1);
+    t.p11 = __ldg(a1 + 1);
+    t.q00 = __ldg(b0);
+    t.q01 = __ldg(b0 + 1);
+    t.q10 = __ldg(b1);
+    t.q11 = __ldg(b1 + 1);
 }
 
 // FarnebackUpdateMatrices for one pixel from its loaded taps
@@ -133,7 +141,7 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
                      long long bwd_stride, int h, int w, int chunk_rows, float clampv) {
     using C = StripCfg<NT>;
     extern __shared__ __align__(16) float smem[];
-    float* ring = smem;                       // [batch % 3][X1..X3][k][col]
+    float* ring = smem;                       // [batch % 3][P0..P2][k][col]: prefix sums of the batch's rows
     float* vbuf = smem + C::RING_FLOATS;      // [buf][row][k][VP]
     const int tid = threadIdx.x;
     const int strip = blockIdx.x >> 1, dir = blockIdx.x & 1;
@@ -168,8 +176,9 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
         const int rowk = i / (2 * C::VPAD), j = i % (2 * C::VPAD);
         vbuf[rowk * C::VP + (j < C::VPAD ? j : NT + j)] = 0.f;
     }
-    // the 13-row window of row r0+j is: suffix X_j of batch b-3 (4-j rows) + batches b-2, b-1 + prefix P_j of batch b.
-    // Every partial sum is formed fresh from at most 4 values, so rounding never accumulates down the chunk.
+    // the 13-row window of row r0+j is: rows j..3 of batch b-3 (its full sum minus its prefix P_{j-1}, kept in the
+    // ring) + batches b-2, b-1 + prefix P_j of batch b.  Every partial sum is formed fresh from at most 4 values, so
+    // rounding never accumulates down the chunk.
     float B1[5], B2[5], B3[5];   // full sums of batches b-1, b-2, b-3
 #pragma unroll
     for (int k = 0; k < 5; ++k) B1[k] = B2[k] = B3[k] = 0.f;
@@ -190,7 +199,7 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
     for (int b = 0; b < n_batches; ++b) {
         float* vb = vbuf + (b & 1) * (IT_RB * 5 * C::VP);
         float* rg = ring + rb * (3 * 5 * NT) + tid;
-        float P[IT_RB][5];
+        float P[5], pold[5];
         // ---- M phase: 4 rows of this thread's column -------------------------------------------------------------
 #pragma unroll
         for (int j = 0; j < IT_RB; ++j) {
@@ -199,24 +208,34 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
             Taps nxt;
             issue_taps(nxt, RP, w, h, gx, row_y(i + 1), fq[j]);
             fq[j] = __ldg(fin + row_y(i + 1 + IT_RB) * w + gx);
+            {
+                // pull the R rows this column will gather from a few rows later into L2 (both images: R0 and R1)
+                const int op = row_y(i + IT_PREFETCH_ROWS) * w + gx;
+                prefetch_l2(RP.R1a + op);
+                prefetch_l2(RP.R0a + op);
+                if ((tid & 3) == 0) { prefetch_l2(RP.R1b + op); prefetch_l2(RP.R0b + op); }
+            }
             float m[5];
             matrix_from_taps(cur, h, sc_x, m);
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                P[j][k] = (j == 0) ? m[k] : P[j - 1][k] + m[k];
-                const float xold = (j == 0) ? B3[k] : rg[((j - 1) * 5 + k) * NT];   // suffix X_j of batch b-3
-                vb[(j * 5 + k) * C::VP + C::VPAD + tid] = (xold + B2[k]) + (B1[k] + P[j][k]);
+                P[k] = (j == 0) ? m[k] : P[k] + m[k];
+                // rows j..3 of batch b-3 = its full sum minus its prefix P_{j-1}; the slot is then reused for batch b
+                float xold = B3[k];
+                if (j > 0) xold -= pold[k];
+                if (j < IT_RB - 1) {
+                    pold[k] = rg[(j * 5 + k) * NT];   // P_j of batch b-3, needed by the next row
+                    rg[(j * 5 + k) * NT] = P[k];
+                }
+                vb[(j * 5 + k) * C::VP + C::VPAD + tid] = (xold + B2[k]) + (B1[k] + P[k]);
             }
             cur = nxt;
         }
-        // publish this batch's suffix sums X1..X3 (X_j = rows j..3 = P3 - P_{j-1}) and rotate the batch sums
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-#pragma unroll
-            for (int j = 1; j < IT_RB; ++j) rg[((j - 1) * 5 + k) * NT] = P[IT_RB - 1][k] - P[j - 1][k];
             B3[k] = B2[k];
             B2[k] = B1[k];
-            B1[k] = P[IT_RB - 1][k];
+            B1[k] = P[k];
         }
         rb = (rb == 2) ? 0 : rb + 1;
         __syncthreads();
@@ -244,13 +263,15 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
                     g[k][i] = acc;
                 }
             }
-            const float scale = 1.f / (float)(IT_WIN * IT_WIN);
+            // OpenCV scales the five sums by 1/169 before the solve; numerator and determinant are both quadratic in
+            // them, so the scale folds into the regulariser: 1e-3 * 169^2
+            const float reg = 1e-3f * (float)(IT_WIN * IT_WIN) * (float)(IT_WIN * IT_WIN);
             float2 o[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float g11 = g[0][i] * scale, g12 = g[1][i] * scale, g22 = g[2][i] * scale;
-                const float h1 = g[3][i] * scale, h2 = g[4][i] * scale;
-                const float idet = 1.f / (diff_of_products(g11, g22, g12, g12) + 1e-3f);
+                const float g11 = g[0][i], g12 = g[1][i], g22 = g[2][i];
+                const float h1 = g[3][i], h2 = g[4][i];
+                const float idet = 1.f / (diff_of_products(g11, g22, g12, g12) + reg);
                 float fx = diff_of_products(g11, h2, g12, h1) * idet;
                 float fy = diff_of_products(g22, h1, g12, h2) * idet;
                 if (clampv > 0.f) {
@@ -281,12 +302,15 @@ static void launch_strip(const float* R, long long img_stride, const float* flow
         attr_set = true;
     }
     const int strips = cdiv(w, C::OUT_W);
-    // rows per chunk: enough CTAs for ~2 waves of 148 SMs x resident CTAs, but chunks no shorter than 48 rows
-    // (12 warm-up rows per chunk) and no longer than 256
-    const int resident = 148 * (NT == 256 ? 2 : 4);
-    int chunks = cdiv(2 * resident, max(1, 2 * strips * n_pairs));
-    chunks = max(1, min(chunks, cdiv(h, 48)));
-    chunks = max(chunks, cdiv(h, 256));
+    // rows per chunk: minimise (waves of resident CTAs) x (rows a CTA marches, incl. its 12 warm-up rows)
+    const long long slots = 148LL * (NT == 256 ? 2 : 4);
+    int chunks = 1;
+    long long best = -1;
+    for (int c = 1; c <= max(1, h / 16); ++c) {
+        const long long ctas = 2LL * strips * c * n_pairs;
+        const long long cost = ((ctas + slots - 1) / slots) * (cdiv(h, c) + 2 * IT_HALO);
+        if (best < 0 || cost < best) { best = cost; chunks = c; }
+    }
     const int chunk_rows = cdiv(h, chunks);
     chunks = cdiv(h, chunk_rows);
     for (int p0 = 0; p0 < n_pairs; p0 += 65535) {

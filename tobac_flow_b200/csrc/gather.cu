@@ -8,6 +8,8 @@
 //
 // One thread per output pixel; the tap stack lives in registers only.  HBM traffic per pixel-step: 3 operand frames
 // (neighbour re-reads hit L1/L2), 2 flow fields (16 B) and the result.
+#include <type_traits>
+
 #include "tf_common.cuh"
 
 namespace tf {
@@ -47,7 +49,7 @@ struct FrameSrc {
     const T* p;   // nullptr -> constant frame
     T fill;
     int H, W;
-    __device__ __forceinline__ T at(int y, int x) const { return p ? p[(long long)y * W + x] : fill; }
+    __device__ __forceinline__ T at(int y, int x) const { return p ? p[y * W + x] : fill; }
 };
 
 // strided view (component c of an interleaved (H, W, 2) flow field) for smooth_flow_step
@@ -55,7 +57,7 @@ struct FlowCompSrc {
     const float* p;
     float fill;
     int H, W;
-    __device__ __forceinline__ float at(int y, int x) const { return p[((long long)y * W + x) * 2]; }
+    __device__ __forceinline__ float at(int y, int x) const { return p[(y * W + x) * 2]; }
 };
 
 __device__ __forceinline__ void cubic_coeffs(int fi, float c[4]) {
@@ -212,6 +214,47 @@ struct RedSobel {
     __device__ __forceinline__ ST finish() const { return (ST)sqrt(gx * gx + gy * gy + gt * gt); }
 };
 
+// Quantised cv2.remap position of one axis: integer part and 1/32 fraction index
+__device__ __forceinline__ void quantise_pos(float p, int& ip, int& fi) {
+    const int s = cv_round_dev(__fmul_rn(p, 32.f));
+    ip = sat_short(s >> 5);
+    fi = s & 31;
+}
+
+// All nine (dx, dy) in {-1,0,1}^2 taps of one warped slab at once (linear interpolation): when the nine sampling
+// positions quantise consistently (same fraction, integer parts one apart - the overwhelmingly common case) and the
+// 4x4 footprint is inside the image, load the 16 texels once and evaluate every tap from registers with exactly the
+// arithmetic of remap_at<TF_LINEAR>.  Returns false when the caller must fall back to per-tap sampling.
+template <typename T>
+__device__ __forceinline__ bool linear_patch9(const T* __restrict__ img, int H, int W, float2 f, int x, int y, T out[9]) {
+    int ix[3], iy[3], fx[3], fy[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        quantise_pos(__fadd_rn(__fadd_rn(f.x, (float)(d - 1)), (float)x), ix[d], fx[d]);
+        quantise_pos(__fadd_rn(__fadd_rn(f.y, (float)(d - 1)), (float)y), iy[d], fy[d]);
+    }
+    const bool ok = fx[0] == fx[1] && fx[2] == fx[1] && fy[0] == fy[1] && fy[2] == fy[1] && ix[0] == ix[1] - 1 &&
+                    ix[2] == ix[1] + 1 && iy[0] == iy[1] - 1 && iy[2] == iy[1] + 1 && ix[0] >= 0 && ix[2] + 1 < W &&
+                    iy[0] >= 0 && iy[2] + 1 < H;
+    if (!ok) return false;
+    const float wfx = (float)fx[1] * (1.0f / 32.0f), wfy = (float)fy[1] * (1.0f / 32.0f);
+    const float wx0 = 1.f - wfx, wy0 = 1.f - wfy;
+    const T w00 = (T)(wy0 * wx0), w01 = (T)(wy0 * wfx), w10 = (T)(wfy * wx0), w11 = (T)(wfy * wfx);
+    T p[4][4];
+    const T* base = img + iy[0] * W + ix[0];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) p[r][c] = base[r * W + c];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+            out[dy * 3 + dx] = add_rn(add_rn(add_rn(mul_rn(p[dy][dx], w00), mul_rn(p[dy][dx + 1], w01)),
+                                             mul_rn(p[dy + 1][dx], w10)), mul_rn(p[dy + 1][dx + 1], w11));
+    return true;
+}
+
 template <typename SrcT, typename ST, int INTERP, int RC>
 __global__ void __launch_bounds__(256) sl_gather_kernel(GatherArgs a) {
     const int x = blockIdx.x * 32 + threadIdx.x;
@@ -220,14 +263,16 @@ __global__ void __launch_bounds__(256) sl_gather_kernel(GatherArgs a) {
     if (x >= a.W || y >= a.H) return;
     const int H = a.H, W = a.W;
     const long long hw = (long long)H * W;
-    const long long pix = (long long)y * W + x;
+    const int pix = y * W + x;
     const SrcT* cur = reinterpret_cast<const SrcT*>(a.cur0) + (long long)t * hw;
     const SrcT fill_s = fill_cast<SrcT>(a.fill);
     const ST fill_st = fill_cast<ST>(a.fill);
-    FrameSrc<SrcT> prev{(t > 0 || a.has_prev) ? cur - hw : nullptr, fill_s, H, W};
-    FrameSrc<SrcT> next{(t < a.n_frames - 1 || a.has_next) ? cur + hw : nullptr, fill_s, H, W};
-    const float2 bf = a.bflow0[(long long)t * hw + pix];
-    const float2 ff = a.fflow0[(long long)t * hw + pix];
+    const FrameSrc<SrcT> prev{(t > 0 || a.has_prev) ? cur - hw : nullptr, fill_s, H, W};
+    const FrameSrc<SrcT> next{(t < a.n_frames - 1 || a.has_next) ? cur + hw : nullptr, fill_s, H, W};
+    const unsigned structure = a.structure;
+    float2 bf = make_float2(0.f, 0.f), ff = make_float2(0.f, 0.f);
+    if (structure & 0x1ffu) bf = __ldg(a.bflow0 + (long long)t * hw + pix);
+    if (structure & (0x1ffu << 18)) ff = __ldg(a.fflow0 + (long long)t * hw + pix);
     const SrcT centre_src = cur[pix];
 
     RedNone<ST> rn{reinterpret_cast<ST*>(a.out) + (long long)t * hw, a.out_tap_stride, pix};
@@ -239,26 +284,32 @@ __global__ void __launch_bounds__(256) sl_gather_kernel(GatherArgs a) {
     if (RC == RC_SOBEL) rsob.init(a.reducer, cast_to<SrcT, ST>(centre_src));
 
     int n = 0;
-#pragma unroll 1
+#pragma unroll
     for (int slab = 0; slab < 3; ++slab) {
-        const unsigned bits = (a.structure >> (9 * slab)) & 0x1ffu;
+        const unsigned bits = (structure >> (9 * slab)) & 0x1ffu;
         if (!bits) continue;
-#pragma unroll 1
+        const float2 f = slab == 0 ? bf : ff;
+        const FrameSrc<SrcT>& src = slab == 0 ? prev : next;
+        SrcT patch[9];
+        bool have_patch = false;
+        if constexpr (INTERP == TF_LINEAR && !std::is_same<SrcT, int>::value) {
+            if (slab != 1 && bits == 0x1ffu && src.p != nullptr) have_patch = linear_patch9<SrcT>(src.p, H, W, f, x, y, patch);
+        }
+#pragma unroll
         for (int j = 0; j < 9; ++j) {
             if (!((bits >> j) & 1u)) continue;
             const int dy = j / 3 - 1, dx = j % 3 - 1;
             ST v;
             if (slab == 1) {
                 const int yy = y + dy, xx = x + dx;
-                v = ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) ? cast_to<SrcT, ST>(cur[(long long)yy * W + xx])
-                                                                                 : fill_st;
+                v = ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) ? cast_to<SrcT, ST>(cur[yy * W + xx]) : fill_st;
+            } else if (have_patch) {
+                v = cast_to<SrcT, ST>(patch[j]);
             } else {
-                const float2 f = slab == 0 ? bf : ff;
                 // p = fl32(fl32(flow + offset) + grid)   (convolve.py:56-63)
                 const float px = __fadd_rn(__fadd_rn(f.x, (float)dx), (float)x);
                 const float py = __fadd_rn(__fadd_rn(f.y, (float)dy), (float)y);
-                const SrcT sv = slab == 0 ? remap_at<INTERP, SrcT>(prev, px, py) : remap_at<INTERP, SrcT>(next, px, py);
-                v = cast_to<SrcT, ST>(sv);
+                v = cast_to<SrcT, ST>(remap_at<INTERP, SrcT>(src, px, py));
             }
             const int k = slab * 9 + j;
             if (RC == RC_NONE) rn.add(n, k, v);
