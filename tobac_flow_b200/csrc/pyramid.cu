@@ -57,6 +57,71 @@ __global__ void __launch_bounds__(256) blur_v_kernel(const uint8_t* __restrict__
     tmp[((long long)img * (h * rp) + r) * W + x] = acc;
 }
 
+// pass A, 4 columns per thread (W % 4 == 0): one 32-bit load per tap row, float4 store
+__global__ void __launch_bounds__(256) blur_v4_kernel(const uint8_t* __restrict__ q0, const uint8_t* __restrict__ q1,
+                                                      float* __restrict__ tmp, int H, int W, int h, int rp,
+                                                      double scale_y, BlurTaps taps) {
+    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;   // group of 4 columns
+    const int r = blockIdx.y;
+    const int img = blockIdx.z;
+    const int W4 = W >> 2;
+    if (x4 >= W4) return;
+    const uchar4* src = reinterpret_cast<const uchar4*>(((img & 1) ? q1 : q0) + (long long)(img >> 1) * H * W);
+    int sy;
+    if (rp == 1) {
+        sy = r;
+    } else {
+        int y0, y1; float fy;
+        resize_coord(r >> 1, scale_y, H, y0, y1, fy);
+        sy = (r & 1) ? y1 : y0;
+    }
+    const int rad = taps.ksize >> 1;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool interior = sy - rad >= 0 && sy + rad < H;
+    for (int k = 0; k < taps.ksize; ++k) {
+        const int yy = interior ? sy + k - rad : reflect101(sy + k - rad, H);
+        const uchar4 c = __ldg(src + yy * W4 + x4);
+        const float wk = taps.w[k];
+        acc.x += wk * (float)c.x;
+        acc.y += wk * (float)c.y;
+        acc.z += wk * (float)c.z;
+        acc.w += wk * (float)c.w;
+    }
+    reinterpret_cast<float4*>(tmp + ((long long)img * (h * rp) + r) * W)[x4] = acc;
+}
+
+// pass B at the full-resolution level (w == W, no resize), 4 outputs per thread (W % 4 == 0)
+__global__ void __launch_bounds__(256) blur_h4_fullres_kernel(const float* __restrict__ tmp, float* __restrict__ out, int W,
+                                                              int h, BlurTaps taps) {
+    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int img = blockIdx.z;
+    const int W4 = W >> 2;
+    if (x4 >= W4) return;
+    const float* row = tmp + ((long long)img * h + j) * W;
+    const int rad = taps.ksize >> 1;
+    const int xb = 4 * x4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (taps.ksize == 3 && xb >= 1 && xb + 4 < W) {
+        const float4 m = reinterpret_cast<const float4*>(row)[x4];
+        const float l = row[xb - 1], rr = row[xb + 4];
+        const float w0 = taps.w[0], w1 = taps.w[1], w2 = taps.w[2];
+        acc.x = (w0 * l + w1 * m.x) + w2 * m.y;
+        acc.y = (w0 * m.x + w1 * m.y) + w2 * m.z;
+        acc.z = (w0 * m.y + w1 * m.z) + w2 * m.w;
+        acc.w = (w0 * m.z + w1 * m.w) + w2 * rr;
+    } else {
+        for (int k = 0; k < taps.ksize; ++k) {
+            const float wk = taps.w[k];
+            acc.x += wk * row[reflect101(xb + k - rad, W)];
+            acc.y += wk * row[reflect101(xb + 1 + k - rad, W)];
+            acc.z += wk * row[reflect101(xb + 2 + k - rad, W)];
+            acc.w += wk * row[reflect101(xb + 3 + k - rad, W)];
+        }
+    }
+    reinterpret_cast<float4*>(out + ((long long)img * h + j) * W)[x4] = acc;
+}
+
 // pass B.  out: (n_img, h, w) fp32
 __global__ void __launch_bounds__(256) blur_h_resize_kernel(const float* __restrict__ tmp, float* __restrict__ out, int W,
                                                             int h, int w, int rp, double scale_x, double scale_y,
@@ -141,12 +206,25 @@ int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int 
     LaunchTimer lt(KC_PYRAMID, (2.0 * H * W + 8.0 * h * w) * n_pairs, s, 2 * cdiv(n_img, 65534));
     for (int z0 = 0; z0 < n_img; z0 += 65534) {
         const int nz = min(n_img - z0, 65534);  // even, so image parity is preserved
-        dim3 ga(cdiv(W, 256), h * rp, nz);
-        blur_v_kernel<<<ga, 256, 0, s>>>(q0 + (long long)(z0 / 2) * H * W, q1 + (long long)(z0 / 2) * H * W,
-                                         tmp + (long long)z0 * h * rp * W, H, W, h, rp, sy, taps);
-        dim3 gb(cdiv(w, 256), h, nz);
-        blur_h_resize_kernel<<<gb, 256, 0, s>>>(tmp + (long long)z0 * h * rp * W, out + (long long)z0 * h * w, W, h, w, rp,
-                                                sx, sy, H, taps);
+        const uint8_t* a0 = q0 + (long long)(z0 / 2) * H * W;
+        const uint8_t* a1 = q1 + (long long)(z0 / 2) * H * W;
+        float* tz = tmp + (long long)z0 * h * rp * W;
+        const bool vec4 = (W % 4 == 0) && (((uintptr_t)a0 | (uintptr_t)a1) % 4 == 0) && ((uintptr_t)tz % 16 == 0);
+        if (vec4) {
+            dim3 ga(cdiv(W / 4, 128), h * rp, nz);
+            blur_v4_kernel<<<ga, 128, 0, s>>>(a0, a1, tz, H, W, h, rp, sy, taps);
+        } else {
+            dim3 ga(cdiv(W, 256), h * rp, nz);
+            blur_v_kernel<<<ga, 256, 0, s>>>(a0, a1, tz, H, W, h, rp, sy, taps);
+        }
+        float* oz = out + (long long)z0 * h * w;
+        if (vec4 && w == W && rp == 1 && (uintptr_t)oz % 16 == 0) {
+            dim3 gb(cdiv(W / 4, 128), h, nz);
+            blur_h4_fullres_kernel<<<gb, 128, 0, s>>>(tz, oz, W, h, taps);
+        } else {
+            dim3 gb(cdiv(w, 256), h, nz);
+            blur_h_resize_kernel<<<gb, 256, 0, s>>>(tz, oz, W, h, w, rp, sx, sy, H, taps);
+        }
     }
     return check_launch("pyramid level");
 }

@@ -81,6 +81,18 @@ def _to_device(data, dtype=None):
     return t.contiguous(), host
 
 
+def _to_host(t: torch.Tensor) -> np.ndarray:
+    """Device tensor -> numpy through page-locked memory (torch caches the pinned block, so repeated calls neither
+    page-fault a fresh pageable array nor re-register memory); the array keeps the pinned storage alive."""
+    if not t.is_cuda:
+        return t.numpy()
+    t = t.contiguous()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()
+
+
 def _dtype_code(np_dtype):
     """``dtype=`` of the reference (a numpy dtype or None -> float64, np.full semantics) -> (torch dtype, code)."""
     dt = np.dtype(np.float64 if np_dtype is None else np_dtype)
@@ -253,13 +265,13 @@ class Flow:
     @property
     def forward_flow(self) -> np.ndarray:
         if self._fwd_np is None:
-            self._fwd_np = self._fwd_t.detach().cpu().numpy()
+            self._fwd_np = _to_host(self._fwd_t.detach())
         return self._fwd_np
 
     @property
     def backward_flow(self) -> np.ndarray:
         if self._bwd_np is None:
-            self._bwd_np = self._bwd_t.detach().cpu().numpy()
+            self._bwd_np = _to_host(self._bwd_t.detach())
         return self._bwd_np
 
     @property
@@ -303,7 +315,7 @@ class Flow:
         else:
             res = convolve_device(t, self.forward_flow_device, self.backward_flow_device, structure, method,
                                   fill_value, dtype, reducer)
-        return res.cpu().numpy() if from_host else res
+        return _to_host(res) if from_host else res
 
     def _convolve_python_func(self, t, structure, method, fill_value, dtype, func):
         """Compatibility path for arbitrary Python reducers: the tap stack of each step is gathered by the
