@@ -301,3 +301,54 @@ def test_growth_marker_masks_bit_exact(tfb, golden):
     assert np.array_equal(np.packbits(filtered >= 0.25), g["mask025"])
     assert np.array_equal(np.packbits(filtered >= 0.5), g["mask05"])
     assert (filtered >= 0.5).sum() > 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# time sharding on one GPU: two shards computed one after the other with the halos filled by hand (the NCCL
+# exchange itself is covered by the gloo tests and by the multi-GPU bench) must reproduce the unsharded result
+# ------------------------------------------------------------------------------------------------------------------
+def test_two_emulated_shards_equal_unsharded(tfb):
+    import torch
+    from tobac_flow_b200 import distributed as D, _lib
+    bt = synthetic.bt_sequence(7, 96, 140, seed=21, nans=True)
+    bt[3, 10:14] = np.nan
+    full = tfb.create_flow(bt)
+    s_diff = np.zeros((3, 3, 3))
+    s_diff[:, 1, 1] = 1
+    want_diff = full.diff(bt)
+    want_sobel = full.sobel(bt)
+    dev = torch.device("cuda")
+    frames = torch.from_numpy(bt).to(dev)
+    world = 2
+    shards = [D.make_shard(frames[slice(*D.shard_bounds(7, world, r))], r, world) for r in range(world)]
+    # halo frames (what exchange_halos moves)
+    shards[0].buf[-1] = shards[1].buf[1]
+    shards[1].buf[0] = shards[0].buf[-2]
+    T0 = shards[0].local.shape[0]
+    # rank 0 produced backward_flow of rank 1's first frame in its extra slot
+    fw0 = torch.full((T0, 96, 140, 2), float("nan"), device=dev)
+    bw0 = torch.full((T0 + 1, 96, 140, 2), float("nan"), device=dev)
+    D.CudaOps().calculate_flow(shards[0].buf[1:T0 + 2], fw0, bw0, 0, "linear", 20)
+    bwd_handover = bw0[T0].clone()
+    T1 = shards[1].local.shape[0]
+    fw1 = torch.full((T1, 96, 140, 2), float("nan"), device=dev)
+    bw1 = torch.full((T1 + 1, 96, 140, 2), float("nan"), device=dev)
+    D.CudaOps().calculate_flow(shards[1].buf[1:T1 + 1], fw1, bw1, 0, "linear", 20)
+    bw1[0] = bwd_handover
+    D.CudaOps().finalise(fw0, bw0[:T0], 20, False, True, False)
+    D.CudaOps().finalise(fw1, bw1[:T1], 20, False, False, True)
+    got_f = torch.cat([fw0, fw1]).cpu().numpy()
+    got_b = torch.cat([bw0[:T0], bw1[:T1]]).cpu().numpy()
+    assert np.array_equal(got_f, full.forward_flow) and np.array_equal(got_b, full.backward_flow)
+    fl0 = D.ShardedFlow(fw0, bw0[:T0], 0, world)
+    fl1 = D.ShardedFlow(fw1, bw1[:T1], 1, world)
+    d = torch.cat([fl0.convolve(shards[0], s_diff, reducer=_lib.TF_RED_DIFF, exchange=False),
+                   fl1.convolve(shards[1], s_diff, reducer=_lib.TF_RED_DIFF, exchange=False)]).cpu().numpy()
+    s = torch.cat([fl0.convolve(shards[0], np.ones((3, 3, 3)), dtype=None, reducer=_lib.TF_RED_SOBEL, exchange=False),
+                   fl1.convolve(shards[1], np.ones((3, 3, 3)), dtype=None, reducer=_lib.TF_RED_SOBEL, exchange=False)]
+                  ).cpu().numpy()
+    assert np.array_equal(d, want_diff, equal_nan=True)
+    assert np.array_equal(s, want_sobel, equal_nan=True)
+    # world == 1 goes through create_flow_sharded itself
+    one = D.create_flow_sharded(D.make_shard(frames, 0, 1))
+    assert np.array_equal(one.fwd.cpu().numpy(), full.forward_flow) and np.array_equal(one.bwd.cpu().numpy(), full.backward_flow)
