@@ -1,0 +1,95 @@
+"""GPU parity at BASELINE.json's full frame sizes (C2 CONUS 1500x2500, C3 500x500, C4 3712x3712, C5 5424x5424).
+
+The oracle's cv2 back-end (the real OpenCV routines the reference calls) finishes one pair / a few frames at these
+sizes in seconds to a minute, so the flows are compared against it directly; everything else is checked through
+size-independent properties (batch-composition independence, clamp bounds, end rules)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import flow_ops as ops  # noqa: E402
+from tobac_flow_b200 import synthetic  # noqa: E402
+
+BACKEND = "cv2" if ops.have_cv2() else "numpy"
+
+
+@pytest.fixture(scope="module")
+def tfb():
+    import tobac_flow_b200
+    return tobac_flow_b200
+
+
+def epe(a, b):
+    return np.sqrt(((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2).sum(-1))
+
+
+def check_flow(mine, ref):
+    e = epe(mine, ref)
+    assert np.isfinite(e).all()
+    # north_star gate: mean <= 0.05 px, p99 <= 0.5 px; we hold a 10x tighter line
+    assert e.mean() <= 5e-3 and np.percentile(e, 99) <= 5e-2, (e.mean(), np.percentile(e, 99), e.max())
+    return e
+
+
+def test_conus_pair_flow_vs_opencv(tfb):
+    bt = synthetic.bt_sequence(3, 1500, 2500, seed=1234, nans=True)[1:]      # frames 1, 2 (with NaN pixels)
+    bt[0, 500:516] = np.nan                                                   # a missing stripe
+    f = tfb.create_flow(bt)
+    rf, rb = ops.create_flow(bt, backend=BACKEND)
+    e1 = check_flow(f.forward_flow, rf)
+    e2 = check_flow(f.backward_flow, rb)
+    print("CONUS EPE mean/p99/max fwd", e1.mean(), np.percentile(e1, 99), e1.max(), "bwd", e2.mean(), e2.max())
+    assert np.abs(f.forward_flow).max() <= 20 and np.abs(f.backward_flow).max() <= 20
+    assert np.array_equal(f.forward_flow[-1], -f.backward_flow[-1])
+    assert np.array_equal(f.backward_flow[0], -f.forward_flow[0])
+
+
+def test_conus_stencils_vs_opencv_remap(tfb):
+    bt = synthetic.bt_sequence(3, 1500, 2500, seed=99, nans=True)
+    rf, rb = ops.create_flow(bt[:2], backend=BACKEND)
+    fwd = np.stack([rf[0], rf[0], rf[1]])
+    bwd = np.stack([rb[0], rb[1], rb[1]])
+    fl = tfb.Flow(fwd, bwd)
+    assert np.array_equal(fl.diff(bt), ops.diff(bt, fwd, bwd, backend=BACKEND), equal_nan=True)
+    got = fl.sobel(bt)[1]
+    s_full = np.ones((3, 3, 3))
+    want = ops.sobel_reducer(None)(ops.tap_stack(bt[0], bt[1], bt[2], fwd[1], bwd[1], s_full, "linear", np.float64,
+                                                 np.nan, BACKEND))
+    want[np.isnan(bt[1])] = np.nan
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    m = ~np.isnan(want)
+    assert np.max(np.abs(got[m] - want[m]) / np.maximum(np.abs(want[m]), 1)) < 1e-12
+    c = fl.convolve(bt)[:, 1]
+    s_cross = np.zeros((3, 3, 3))
+    s_cross[1, 1, :] = s_cross[1, :, 1] = s_cross[:, 1, 1] = 1
+    assert np.array_equal(c, ops.tap_stack(bt[0], bt[1], bt[2], fwd[1], bwd[1], s_cross, "linear", np.float32, np.nan,
+                                           BACKEND), equal_nan=True)
+
+
+def test_mesoscale_500_sequence_vs_opencv(tfb):
+    bt = synthetic.bt_sequence(6, 500, 500, seed=1236, nans=True)
+    f = tfb.create_flow(bt)
+    rf, rb = ops.create_flow(bt, backend=BACKEND)
+    check_flow(f.forward_flow, rf)
+    check_flow(f.backward_flow, rb)
+
+
+@pytest.mark.parametrize("shape", [(3712, 3712), (5424, 5424)])
+def test_full_disk_pair_vs_opencv_and_batch_independence(tfb, shape):
+    import torch
+    h, w = shape
+    base = synthetic.base_field(h, w, 1237)
+    cores = synthetic.core_table(4, h, w, 1237)
+    bt = np.stack([synthetic.bt_frame(base, t, cores, None, 4) for t in (1, 2)])
+    f = tfb.create_flow(bt)
+    rf, rb = ops.create_flow(bt, backend=BACKEND)
+    check_flow(f.forward_flow, rf)
+    check_flow(f.backward_flow, rb)
+    # the same pair inside a larger batch must give the same bits (no cross-pair coupling, no atomics in the math)
+    seq = np.stack([bt[0], bt[1], bt[0], bt[1]])
+    g = tfb.create_flow(seq)
+    assert np.array_equal(g.forward_flow[0], f.forward_flow[0]) and np.array_equal(g.forward_flow[2], f.forward_flow[0])
+    assert np.array_equal(g.backward_flow[1], f.backward_flow[1]) and np.array_equal(g.backward_flow[3], f.backward_flow[1])
+    del f, g
+    torch.cuda.empty_cache()

@@ -182,8 +182,10 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
     float B1[5], B2[5], B3[5];   // full sums of batches b-1, b-2, b-3
 #pragma unroll
     for (int k = 0; k < 5; ++k) B1[k] = B2[k] = B3[k] = 0.f;
-    const int r_begin = yc0 - IT_HALO;
-    const int n_rows = (yc1 - yc0) + 2 * IT_HALO;
+    // batches of 4 rows are aligned to absolute image rows, so the partial sums a window is built from (and hence
+    // the result bits) do not depend on where the chunk starts, i.e. on the launch geometry / batch size
+    const int r_begin = (((yc0 - IT_HALO + 8) >> 2) << 2) - 8;
+    const int n_rows = (yc1 + IT_HALO) - r_begin;
     const int n_batches = (n_rows + IT_RB - 1) / IT_RB;
     int rb = 0;                  // ring slot of batch b (b % 3): overwritten at the end of the batch, read as b-3 first
 
