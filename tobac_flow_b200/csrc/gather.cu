@@ -172,7 +172,8 @@ struct RedDiff {
         const ST s = (is_nan(a) ? (ST)0 : a) + (is_nan(b) ? (ST)0 : b);
         int cnt = (is_fin(x[2]) ? 1 : 0) + (is_fin(x[0]) ? 1 : 0);
         cnt = max(cnt, 1);
-        return (ST)((double)s / (double)cnt);
+        // numpy divides through fp64 and rounds back; dividing by 1 or 2 is exact in any precision
+        return cnt == 2 ? s * (ST)0.5 : s;
     }
 };
 
@@ -255,7 +256,15 @@ __device__ __forceinline__ bool linear_patch9(const T* __restrict__ img, int H, 
     return true;
 }
 
-template <typename SrcT, typename ST, int INTERP, int RC>
+// Structures the reference and its callers actually use get kernels with the 3x3x3 mask as a compile-time constant
+// (SB != 0): the 27-tap walk then unrolls to exactly the taps present.
+constexpr unsigned SB_T3 = (1u << 4) | (1u << 13) | (1u << 22);                       // Flow.diff, filtered_tdiff
+constexpr unsigned SB_CROSS7 = SB_T3 | (1u << 10) | (1u << 12) | (1u << 14) | (1u << 16);  // generate_binary_structure(3, 1)
+constexpr unsigned SB_S5 = (1u << 10) | (1u << 12) | (1u << 13) | (1u << 14) | (1u << 16); // same-step cross
+constexpr unsigned SB_L2 = (1u << 4) | (1u << 22);                                    // label.py:133-137
+constexpr unsigned SB_FULL = (1u << 27) - 1u;                                           // sobel
+
+template <typename SrcT, typename ST, int INTERP, int RC, unsigned SB>
 __global__ void __launch_bounds__(256) sl_gather_kernel(GatherArgs a) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
@@ -269,7 +278,7 @@ __global__ void __launch_bounds__(256) sl_gather_kernel(GatherArgs a) {
     const ST fill_st = fill_cast<ST>(a.fill);
     const FrameSrc<SrcT> prev{(t > 0 || a.has_prev) ? cur - hw : nullptr, fill_s, H, W};
     const FrameSrc<SrcT> next{(t < a.n_frames - 1 || a.has_next) ? cur + hw : nullptr, fill_s, H, W};
-    const unsigned structure = a.structure;
+    const unsigned structure = SB ? SB : a.structure;
     float2 bf = make_float2(0.f, 0.f), ff = make_float2(0.f, 0.f);
     if (structure & 0x1ffu) bf = __ldg(a.bflow0 + (long long)t * hw + pix);
     if (structure & (0x1ffu << 18)) ff = __ldg(a.fflow0 + (long long)t * hw + pix);
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(256) sl_gather_kernel(GatherArgs a) {
 
 static thread_local double g_gather_bytes = 0;
 
-template <typename SrcT, typename ST, int INTERP, int RC>
+template <typename SrcT, typename ST, int INTERP, int RC, unsigned SB = 0u>
 static int launch_gather(const GatherArgs& a, cudaStream_t s) {
     dim3 block(32, 8);
     {
@@ -353,7 +362,7 @@ static int launch_gather(const GatherArgs& a, cudaStream_t s) {
         b.has_prev = (t0 > 0) ? 1 : a.has_prev;
         b.has_next = (t0 + nt < a.n_frames) ? 1 : a.has_next;
         dim3 grid(cdiv(a.W, 32), cdiv(a.H, 8), nt);
-        sl_gather_kernel<SrcT, ST, INTERP, RC><<<grid, block, 0, s>>>(b);
+        sl_gather_kernel<SrcT, ST, INTERP, RC, SB><<<grid, block, 0, s>>>(b);
     }
     return check_launch("tf_sl_convolve");
 }
@@ -464,12 +473,29 @@ extern "C" int tf_sl_convolve(const void* cur0, int n_frames, int has_prev, int 
     if (src_dtype == TF_I32) {
         if (interp != TF_NEAREST) { set_error("tf_sl_convolve: integer operands support nearest interpolation only (as cv2.remap)"); return TF_ERR_UNSUPPORTED; }
         if (stack_dtype != TF_I32) { set_error("tf_sl_convolve: integer operands need an int32 result dtype"); return TF_ERR_UNSUPPORTED; }
+        if (rc == RC_NONE && a.structure == SB_L2) return launch_gather<int, int, TF_NEAREST, RC_NONE, SB_L2>(a, s);
+        if (rc == RC_STAT && reducer == TF_RED_ANY && a.structure == SB_T3)
+            return launch_gather<int, int, TF_NEAREST, RC_STAT, SB_T3>(a, s);
         if (rc == RC_NONE) return launch_gather<int, int, TF_NEAREST, RC_NONE>(a, s);
         if (rc == RC_STAT && (reducer == TF_RED_ANY || reducer == TF_RED_NANMAX || reducer == TF_RED_NANMIN))
             return launch_gather<int, int, TF_NEAREST, RC_STAT>(a, s);
         set_error("tf_sl_convolve: reducer %d is not available for int32 operands", reducer);
         return TF_ERR_UNSUPPORTED;
     }
+    // compile-time structures for the combinations on the reference's call paths
+    const unsigned sb = a.structure;
+    const bool f32 = src_dtype == TF_F32, f64s = src_dtype == TF_F64, st32 = stack_dtype == TF_F32, st64 = stack_dtype == TF_F64;
+    if (interp == TF_LINEAR) {
+        if (f32 && st32 && rc == RC_DIFF && sb == SB_T3) return launch_gather<float, float, TF_LINEAR, RC_DIFF, SB_T3>(a, s);
+        if (f32 && st32 && rc == RC_STAT && sb == SB_T3) return launch_gather<float, float, TF_LINEAR, RC_STAT, SB_T3>(a, s);
+        if (f64s && st32 && rc == RC_STAT && sb == SB_T3) return launch_gather<double, float, TF_LINEAR, RC_STAT, SB_T3>(a, s);
+        if (f32 && st32 && rc == RC_STAT && sb == SB_S5) return launch_gather<float, float, TF_LINEAR, RC_STAT, SB_S5>(a, s);
+        if (f32 && st64 && rc == RC_SOBEL && sb == SB_FULL) return launch_gather<float, double, TF_LINEAR, RC_SOBEL, SB_FULL>(a, s);
+        if (f32 && st32 && rc == RC_SOBEL && sb == SB_FULL) return launch_gather<float, float, TF_LINEAR, RC_SOBEL, SB_FULL>(a, s);
+        if (f32 && st32 && rc == RC_NONE && sb == SB_CROSS7) return launch_gather<float, float, TF_LINEAR, RC_NONE, SB_CROSS7>(a, s);
+    }
+    if (interp == TF_CUBIC && f32 && st64 && rc == RC_SOBEL && sb == SB_FULL)
+        return launch_gather<float, double, TF_CUBIC, RC_SOBEL, SB_FULL>(a, s);
     if (src_dtype == TF_F32 && stack_dtype == TF_F32) return dispatch_interp<float, float>(a, interp, rc, s);
     if (src_dtype == TF_F32 && stack_dtype == TF_F64) return dispatch_interp<float, double>(a, interp, rc, s);
     if (src_dtype == TF_F64 && stack_dtype == TF_F32) return dispatch_interp<double, float>(a, interp, rc, s);
