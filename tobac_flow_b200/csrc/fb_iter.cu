@@ -18,12 +18,17 @@
 //   * forward and backward CTAs of the same pair and strip are adjacent in launch order, so the second reader of the
 //     shared R planes hits L2.
 // Algorithmic HBM bytes per pixel-iteration: flow 8 + R0 20 + R1 20 read, flow 8 written = 56 B.
+#include <stdlib.h>
+
 #include "farneback_internal.cuh"
 
 namespace tf {
 
 constexpr int IT_HALO = 6, IT_WIN = 13, IT_RB = 4;
-constexpr int IT_PREFETCH_ROWS = 6;
+#ifndef TF_L2_PREFETCH_ROWS
+#define TF_L2_PREFETCH_ROWS 0
+#endif
+constexpr int IT_PREFETCH_ROWS = TF_L2_PREFETCH_ROWS;   // measured: no gain on B200, so off
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -210,7 +215,7 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
             Taps nxt;
             issue_taps(nxt, RP, w, h, gx, row_y(i + 1), fq[j]);
             fq[j] = __ldg(fin + row_y(i + 1 + IT_RB) * w + gx);
-            {
+            if (IT_PREFETCH_ROWS > 0) {
                 // pull the R rows this column will gather from a few rows later into L2 (both images: R0 and R1)
                 const int op = row_y(i + IT_PREFETCH_ROWS) * w + gx;
                 prefetch_l2(RP.R1a + op);
@@ -336,7 +341,11 @@ int launch_fb_iteration(const float* R, long long img_stride, const float* flow_
     LaunchTimer lt(full_res ? KC_FB_ITER_L0 : KC_FB_ITER, 56.0 * h * w * 2 * n_pairs, s, cdiv(n_pairs, 65535));
     // strip width: the configuration that wastes fewer columns
     const int pad256 = cdiv(w, StripCfg<256>::OUT_W) * 256, pad128 = cdiv(w, StripCfg<128>::OUT_W) * 128;
-    if (pad256 <= pad128)
+    // 128-column strips (4 resident CTAs per SM) measured faster than 256-column ones (2 per SM) at equal padding:
+    // more independent CTAs hide each other's barrier and gather latency.  256 only when it wastes clearly less.
+    static const char* force_nt = getenv("TF_FORCE_NT");
+    const bool use256 = force_nt ? (atoi(force_nt) == 256) : (10 * pad256 < 9 * pad128);
+    if (use256)
         launch_strip<256>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
     else
         launch_strip<128>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
