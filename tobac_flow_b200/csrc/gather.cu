@@ -196,23 +196,61 @@ struct RedStat {  // nanmean / nanmax / nanmin / any
     }
 };
 
-template <typename ST>
+// Sobel magnitude over the 27 taps (sobel.py:7-86): taps are kept in registers in the stack dtype and reduced at the end.
+// KT: type the taps are kept in = the narrower of operand and stack dtype (the cast to ST is then exact and is redone on use)
+template <typename ST, typename KT>
 struct RedSobel {
-    int dir; ST centre; double gx, gy, gt;
-    __device__ __forceinline__ void init(int d, ST c) { dir = d; centre = c; gx = gy = gt = 0.0; }
-    __device__ __forceinline__ void add(int, int k, ST v) {
-        ST d = v - centre;
-        if (dir == TF_RED_SOBEL_UPHILL) d = is_nan(d) ? (ST)0 : (d > (ST)0 ? d : (ST)0);        // np.fmax(d, 0)
-        else if (dir == TF_RED_SOBEL_DOWNHILL) d = is_nan(d) ? (ST)0 : (d < (ST)0 ? d : (ST)0); // np.fmin(d, 0)
-        if (is_nan(d)) return;
-        const int t = k / 9, y = (k / 3) % 3, x = k % 3;
-        const int wt = 2 - (t - 1) * (t - 1), wy = 2 - (y - 1) * (y - 1), wx = 2 - (x - 1) * (x - 1);  // (1, 2, 1)
-        const double dd = (double)d;
-        gx += dd * (double)(wt * wy * (x - 1));
-        gy += dd * (double)(wx * wt * (y - 1));
-        gt += dd * (double)(wy * wx * (t - 1));
+    int dir; ST centre; KT v[27]; bool any_nan;
+    __device__ __forceinline__ void init(int d, ST c) { dir = d; centre = c; any_nan = false; }
+    __device__ __forceinline__ void add(int, int k, KT val) {
+        v[k] = val;
+        any_nan |= is_nan(val);
     }
-    __device__ __forceinline__ ST finish() const { return (ST)sqrt(gx * gx + gy * gy + gt * gt); }
+    // general form: d_k = v_k - centre (optionally clipped), NaN terms skipped, fp64 sums of d_k * S_k
+    __device__ __forceinline__ ST finish_general() const {
+        double gx = 0.0, gy = 0.0, gt = 0.0;
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+            ST d = (ST)v[k] - centre;
+            if (dir == TF_RED_SOBEL_UPHILL) d = is_nan(d) ? (ST)0 : (d > (ST)0 ? d : (ST)0);        // np.fmax(d, 0)
+            else if (dir == TF_RED_SOBEL_DOWNHILL) d = is_nan(d) ? (ST)0 : (d < (ST)0 ? d : (ST)0); // np.fmin(d, 0)
+            if (is_nan(d)) continue;
+            const int t = k / 9, y = (k / 3) % 3, x = k % 3;
+            const int wt = 2 - (t - 1) * (t - 1), wy = 2 - (y - 1) * (y - 1), wx = 2 - (x - 1) * (x - 1);  // (1, 2, 1)
+            const double dd = (double)d;
+            if (wt * wy * (x - 1) != 0) gx += dd * (double)(wt * wy * (x - 1));
+            if (wx * wt * (y - 1) != 0) gy += dd * (double)(wx * wt * (y - 1));
+            if (wy * wx * (t - 1) != 0) gt += dd * (double)(wy * wx * (t - 1));
+        }
+        return (ST)sqrt(gx * gx + gy * gy + gt * gt);
+    }
+    // plain direction, fp64 stack, no NaN tap: the weights of each gradient sum to zero, so the centre drops out and
+    // the (1,2,1) x (1,2,1) x (-1,0,1) kernels are applied separably to the raw taps.  Every first-level sum /
+    // difference of fp32-valued taps is exact in fp64, so this is at least as accurate as the general form.
+    __device__ __forceinline__ double finish_separable() const {
+        double gxs[3], gys[3], gts[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            double rd[3], rs[3];
+#pragma unroll
+            for (int y = 0; y < 3; ++y) {
+                const double a = (double)v[t * 9 + y * 3], b = (double)v[t * 9 + y * 3 + 1], c = (double)v[t * 9 + y * 3 + 2];
+                rd[y] = c - a;
+                rs[y] = (a + c) + 2.0 * b;
+            }
+            gxs[t] = (rd[0] + rd[2]) + 2.0 * rd[1];
+            gys[t] = rs[2] - rs[0];
+            gts[t] = (rs[0] + rs[2]) + 2.0 * rs[1];
+        }
+        const double gx = (gxs[0] + gxs[2]) + 2.0 * gxs[1];
+        const double gy = (gys[0] + gys[2]) + 2.0 * gys[1];
+        const double gt = gts[2] - gts[0];
+        return sqrt(gx * gx + gy * gy + gt * gt);
+    }
+    __device__ __forceinline__ ST finish() const {
+        if (sizeof(ST) == 8 && dir == TF_RED_SOBEL && !any_nan) return (ST)finish_separable();
+        return finish_general();
+    }
 };
 
 // Quantised cv2.remap position of one axis: integer part and 1/32 fraction index
@@ -287,7 +325,8 @@ __global__ void __launch_bounds__(256) sl_gather_kernel(GatherArgs a) {
     RedNone<ST> rn{reinterpret_cast<ST*>(a.out) + (long long)t * hw, a.out_tap_stride, pix};
     RedDiff<ST> rd;
     RedStat<ST> rs;
-    RedSobel<ST> rsob;
+    typedef typename std::conditional<(sizeof(SrcT) < sizeof(ST)), SrcT, ST>::type KeepT;
+    RedSobel<ST, KeepT> rsob;
     if (RC == RC_DIFF) { rd.x[0] = rd.x[1] = rd.x[2] = (ST)0; }
     if (RC == RC_STAT) rs.init(a.reducer);
     if (RC == RC_SOBEL) rsob.init(a.reducer, cast_to<SrcT, ST>(centre_src));
@@ -324,7 +363,7 @@ __global__ void __launch_bounds__(256) sl_gather_kernel(GatherArgs a) {
             if (RC == RC_NONE) rn.add(n, k, v);
             if (RC == RC_DIFF) rd.add(n, k, v);
             if (RC == RC_STAT) rs.add(n, k, v);
-            if (RC == RC_SOBEL) rsob.add(n, k, v);
+            if (RC == RC_SOBEL) rsob.add(n, k, (KeepT)v);
             ++n;
         }
     }
