@@ -47,13 +47,16 @@ __device__ __forceinline__ float ld_stream1(const float* p) {
     return r;
 }
 
-template <int NT>
+// HK = outputs per thread in the H phase = rows per H phase (4: after every M batch, vertical sums double-buffered;
+// 8: after every second M batch, single buffer, one more barrier).  Same shared-memory footprint either way.
+template <int NT, int HK>
 struct StripCfg {
     static constexpr int OUT_W = NT - 2 * IT_HALO;
     static constexpr int VPAD = 8;
     static constexpr int VP = NT + 2 * VPAD;                 // pitch of a row of vertical sums (zero pads both sides)
     static constexpr int RING_FLOATS = 3 * 3 * 5 * NT;       // 3 batches x prefix sums P0..P2 x 5 channels
-    static constexpr int VBUF_FLOATS = 2 * IT_RB * 5 * VP;   // double-buffered
+    static constexpr int VBUF_ROWS = 8;                      // 2 x 4 (double-buffered) or 1 x 8
+    static constexpr int VBUF_FLOATS = VBUF_ROWS * 5 * VP;
     static constexpr int SMEM_BYTES = (RING_FLOATS + VBUF_FLOATS) * (int)sizeof(float);
 };
 
@@ -154,12 +157,12 @@ __device__ __forceinline__ float diff_of_products(float a, float b, float c, flo
     return dop + err;
 }
 
-template <int NT>
+template <int NT, int HK>
 __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 4))
 fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const float* __restrict__ flow_in,
                      float* __restrict__ out_fwd, long long fwd_stride, float* __restrict__ out_bwd,
                      long long bwd_stride, int h, int w, int chunk_rows, float clampv) {
-    using C = StripCfg<NT>;
+    using C = StripCfg<NT, HK>;
     extern __shared__ __align__(16) float smem[];
     float* ring = smem;                       // [batch % 3][P0..P2][k][col]: prefix sums of the batch's rows
     float* vbuf = smem + C::RING_FLOATS;      // [buf][row][k][VP]
@@ -186,13 +189,13 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
     // M-phase identity: one column of the strip (replicate-clamped = the box filter's border rule)
     const int gx = min(max(x0 - IT_HALO + tid, 0), w - 1);
     const float sc_x = border_factor(gx, w);
-    // H-phase identity: one row of the batch, 4 adjacent output columns
-    const int hr = tid / (NT / 4), cg = tid % (NT / 4);
+    // H-phase identity: one row of the H batch, HK adjacent output columns
+    const int hr = tid / (NT / HK), cg = tid % (NT / HK);
 
     // zero the suffix-sum ring column and the pads of the vertical-sum rows
 #pragma unroll
     for (int s = 0; s < 3 * 3 * 5; ++s) ring[s * NT + tid] = 0.f;
-    for (int i = tid; i < 2 * IT_RB * 5 * 2 * C::VPAD; i += NT) {
+    for (int i = tid; i < C::VBUF_ROWS * 5 * 2 * C::VPAD; i += NT) {
         const int rowk = i / (2 * C::VPAD), j = i % (2 * C::VPAD);
         vbuf[rowk * C::VP + (j < C::VPAD ? j : NT + j)] = 0.f;
     }
@@ -219,7 +222,9 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
     __syncthreads();
 
     for (int b = 0; b < n_batches; ++b) {
-        float* vb = vbuf + (b & 1) * (IT_RB * 5 * C::VP);
+        // rows of the vertical-sum buffer this M batch fills
+        float* vb = vbuf + (HK == 4 ? (b & 1) : 0) * (IT_RB * 5 * C::VP);
+        float* vbm = vbuf + (b & 1) * (IT_RB * 5 * C::VP);
         float* rg = ring + rb * (3 * 5 * NT) + tid;
         float P[5], pold[5];
         // ---- M phase: 4 rows of this thread's column -------------------------------------------------------------
@@ -249,7 +254,7 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
                     pold[k] = rg[(j * 5 + k) * NT];   // P_j of batch b-3, needed by the next row
                     rg[(j * 5 + k) * NT] = P[k];
                 }
-                vb[(j * 5 + k) * C::VP + C::VPAD + tid] = (xold + B2[k]) + (B1[k] + P[k]);
+                vbm[(j * 5 + k) * C::VP + C::VPAD + tid] = (xold + B2[k]) + (B1[k] + P[k]);
             }
             cur = nxt;
         }
@@ -260,18 +265,20 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
             B1[k] = P[k];
         }
         rb = (rb == 2) ? 0 : rb + 1;
+        if (HK == 8 && (b & 1) == 0 && b + 1 < n_batches) continue;   // H phase after every second batch
         __syncthreads();
-        // ---- H phase: row hr of the batch, outputs 4*cg .. 4*cg+3 ------------------------------------------------
-        const int y = r_begin + b * IT_RB + hr - IT_HALO;
-        if (y >= yc0 && y < yc1) {
-            float g[5][4];
+        // ---- H phase: row hr of the H batch, outputs HK*cg .. HK*cg+HK-1 ---------------------------------------
+        const int hb0 = (HK == 8) ? (b & ~1) : b;                      // first M batch covered by this H phase
+        const int y = r_begin + hb0 * IT_RB + hr - IT_HALO;
+        if (y >= yc0 && y < yc1 && (HK == 4 || hr < IT_RB * (b - hb0 + 1))) {
+            float g[5][HK];
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                // v[j] = vertical sum at region column 4*cg - 8 + j
-                const float4* row = reinterpret_cast<const float4*>(vb + (hr * 5 + k) * C::VP + 4 * cg);
-                float v[20];
+                // v[j] = vertical sum at region column HK*cg - 8 + j
+                const float4* row = reinterpret_cast<const float4*>(vb + (hr * 5 + k) * C::VP + HK * cg);
+                float v[HK + 16];
 #pragma unroll
-                for (int q = 0; q < 5; ++q) {
+                for (int q = 0; q < (HK + 16) / 4; ++q) {
                     const float4 t = row[q];
                     v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
                 }
@@ -280,7 +287,7 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
                 for (int j = 2; j < 2 + IT_WIN; ++j) acc += v[j];
                 g[k][0] = acc;
 #pragma unroll
-                for (int i = 1; i < 4; ++i) {
+                for (int i = 1; i < HK; ++i) {
                     acc += v[i + 1 + IT_WIN] - v[i + 1];
                     g[k][i] = acc;
                 }
@@ -288,9 +295,9 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
             // OpenCV scales the five sums by 1/169 before the solve; numerator and determinant are both quadratic in
             // them, so the scale folds into the regulariser: 1e-3 * 169^2
             const float reg = 1e-3f * (float)(IT_WIN * IT_WIN) * (float)(IT_WIN * IT_WIN);
-            float2 o[4];
+            float2 o[HK];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < HK; ++i) {
                 const float g11 = g[0][i], g12 = g[1][i], g22 = g[2][i];
                 const float h1 = g[3][i], h2 = g[4][i];
                 const float idet = 1.f / (diff_of_products(g11, g22, g12, g12) + reg);
@@ -302,25 +309,26 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
                 }
                 o[i] = make_float2(fx, fy);
             }
-            const int c0 = 4 * cg;                         // region column of o[0]
+            const int c0 = HK * cg;                        // region column of o[0]
             const int xg = x0 - IT_HALO + c0;              // image column of o[0]
             float2* dst = fout + (long long)y * w + xg;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < HK; ++i) {
                 const int c = c0 + i;
                 if (c >= IT_HALO && c < NT - IT_HALO && xg + i < w) dst[i] = o[i];
             }
         }
+        if (HK == 8) __syncthreads();   // single vertical-sum buffer: the next M batch overwrites it
     }
 }
 
-template <int NT>
+template <int NT, int HK>
 static void launch_strip(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride,
                          float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, float clamp, cudaStream_t s) {
-    using C = StripCfg<NT>;
+    using C = StripCfg<NT, HK>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(fb_iter_strip_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        cudaFuncSetAttribute(fb_iter_strip_kernel<NT, HK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         attr_set = true;
     }
     const int strips = cdiv(w, C::OUT_W);
@@ -338,7 +346,7 @@ static void launch_strip(const float* R, long long img_stride, const float* flow
     for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
         const int np = min(n_pairs - p0, 65535);
         dim3 g(2 * strips, chunks, np);
-        fb_iter_strip_kernel<NT><<<g, NT, C::SMEM_BYTES, s>>>(R + (long long)(2 * p0) * img_stride, img_stride,
+        fb_iter_strip_kernel<NT, HK><<<g, NT, C::SMEM_BYTES, s>>>(R + (long long)(2 * p0) * img_stride, img_stride,
                                                               flow_in + (long long)(2 * p0) * 2 * h * w,
                                                               out_fwd + p0 * fwd_stride, fwd_stride,
                                                               out_bwd + p0 * bwd_stride, bwd_stride, h, w, chunk_rows, clamp);
@@ -355,15 +363,21 @@ int launch_fb_iteration(const float* R, long long img_stride, const float* flow_
     if ((long long)h * w > 0x3fffffffLL) { set_error("fb iteration: level too large"); return TF_ERR_INVALID_ARGUMENT; }
     LaunchTimer lt(full_res ? KC_FB_ITER_L0 : KC_FB_ITER, 56.0 * h * w * 2 * n_pairs, s, cdiv(n_pairs, 65535));
     // strip width: the configuration that wastes fewer columns
-    const int pad256 = cdiv(w, StripCfg<256>::OUT_W) * 256, pad128 = cdiv(w, StripCfg<128>::OUT_W) * 128;
+    const int pad256 = cdiv(w, StripCfg<256, 4>::OUT_W) * 256, pad128 = cdiv(w, StripCfg<128, 4>::OUT_W) * 128;
+    static const char* force_hk = getenv("TF_FORCE_HK");
+    const bool hk8 = force_hk ? (atoi(force_hk) == 8) : false;
     // 128-column strips (4 resident CTAs per SM) measured faster than 256-column ones (2 per SM) at equal padding:
     // more independent CTAs hide each other's barrier and gather latency.  256 only when it wastes clearly less.
     static const char* force_nt = getenv("TF_FORCE_NT");
     const bool use256 = force_nt ? (atoi(force_nt) == 256) : (10 * pad256 < 9 * pad128);
-    if (use256)
-        launch_strip<256>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
+    if (use256 && hk8)
+        launch_strip<256, 8>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
+    else if (use256)
+        launch_strip<256, 4>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
+    else if (hk8)
+        launch_strip<128, 8>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
     else
-        launch_strip<128>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
+        launch_strip<128, 4>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
     return check_launch("fb iteration");
 }
 
