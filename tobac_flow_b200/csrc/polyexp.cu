@@ -1,90 +1,121 @@
 // K3: Farneback polynomial expansion (OpenCV FarnebackPolyExp, polyN = 5): separable 11-tap tile convolution with
 // replicate borders.  Input level image I (h, w) fp32 -> per image a float4 plane (c0..c3) followed by a float plane
 // (c4), so the iteration kernel's bilinear gathers are one 16-byte and one 4-byte coalesced load per tap.
-// Shared-memory tile with a 5-pixel halo: vertical pass to three moment arrays, horizontal pass to six sums.
+// Shared-memory tile with a 5-pixel halo; both passes are register-blocked (vertical: a 26-row column window per
+// thread for 16 outputs; horizontal: 16 values of each moment row per thread for 4 outputs).
 // HBM traffic: 4 B/px read (+ halo re-reads that hit L2) and 20 B/px written.
 #include "farneback_internal.cuh"
 
 namespace tf {
 
-constexpr int PE_TW = 64, PE_TH = 32, PE_N = 5;
-constexpr int PE_SW = PE_TW + 2 * PE_N;      // 74 columns incl. halo
-constexpr int PE_SWP = PE_SW + 2;            // padded row pitch (76)
-constexpr int PE_SH = PE_TH + 2 * PE_N;      // 42 rows incl. halo
+constexpr int PE_N = 5;
+constexpr int PE_SW = 128;                    // region columns incl. halo (also the shared-memory pitch)
+constexpr int PE_TW = PE_SW - 2 * PE_N;       // 118 output columns per tile
+constexpr int PE_TH = 32;                     // output rows per tile
+constexpr int PE_SH = PE_TH + 2 * PE_N;       // 42 rows incl. halo
+constexpr int PE_VSEG = 16;                   // rows per thread in the vertical pass
+constexpr int PE_SMEM_BYTES = (PE_SH * PE_SW + 3 * PE_TH * PE_SW + 4) * (int)sizeof(float);  // +4: the last group's 16-value load overhangs
 
 __global__ void __launch_bounds__(256) polyexp_kernel(const float* __restrict__ I, float* __restrict__ R,
                                                       long long img_stride, int h, int w, PolyConsts pc) {
-    __shared__ float s_in[PE_SH][PE_SWP];
-    __shared__ float s_v[3][PE_TH][PE_SWP];
+    extern __shared__ __align__(16) float pe_smem[];
+    float (*s_in)[PE_SW] = reinterpret_cast<float (*)[PE_SW]>(pe_smem);
+    float (*s_v)[PE_TH][PE_SW] = reinterpret_cast<float (*)[PE_TH][PE_SW]>(pe_smem + PE_SH * PE_SW);
     const int img = blockIdx.z;
     const int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH;
     const float* src = I + (long long)img * h * w;
     const int tid = threadIdx.x;
 
+    // tile + 5-px halo, replicate-clamped (the clamp IS OpenCV's border rule for both passes)
     for (int idx = tid; idx < PE_SH * PE_SW; idx += 256) {
         const int r = idx / PE_SW, c = idx - r * PE_SW;
         const int gy = min(max(y0 + r - PE_N, 0), h - 1);
         const int gx = min(max(x0 + c - PE_N, 0), w - 1);
-        s_in[r][c] = src[(long long)gy * w + gx];
+        s_in[r][c] = src[gy * w + gx];
     }
     __syncthreads();
 
-    // vertical pass (fp32, same accumulation order as OpenCV: k = 1..n)
-    for (int idx = tid; idx < PE_TH * PE_SW; idx += 256) {
-        const int r = idx / PE_SW, c = idx - r * PE_SW;
-        // replicate in y is relative to the IMAGE, which the clamped tile load already provides
-        const float ctr = s_in[r + PE_N][c];
-        float t0 = ctr * pc.g[0], t1 = 0.f, t2 = 0.f;
+    // vertical pass: one thread per (column, 16-row segment), the 26 input rows it needs held in registers;
+    // fp32, accumulation order of OpenCV (k = 1..n)
+    {
+        const int c = tid & (PE_SW - 1), seg = tid >> 7;
+        float in[PE_VSEG + 2 * PE_N];
 #pragma unroll
-        for (int k = 1; k <= PE_N; ++k) {
-            const float a = s_in[r + PE_N - k][c], b = s_in[r + PE_N + k][c];
-            const float p = a + b;
-            t0 = t0 + pc.g[k] * p;
-            t1 = t1 + pc.xg[k] * (b - a);
-            t2 = t2 + pc.xxg[k] * p;
+        for (int i = 0; i < PE_VSEG + 2 * PE_N; ++i) in[i] = s_in[seg * PE_VSEG + i][c];
+#pragma unroll
+        for (int r = 0; r < PE_VSEG; ++r) {
+            float t0 = in[r + PE_N] * pc.g[0], t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= PE_N; ++k) {
+                const float a = in[r + PE_N - k], b = in[r + PE_N + k];
+                const float p = a + b;
+                t0 = t0 + pc.g[k] * p;
+                t1 = t1 + pc.xg[k] * (b - a);
+                t2 = t2 + pc.xxg[k] * p;
+            }
+            s_v[0][seg * PE_VSEG + r][c] = t0;
+            s_v[1][seg * PE_VSEG + r][c] = t1;
+            s_v[2][seg * PE_VSEG + r][c] = t2;
         }
-        s_v[0][r][c] = t0;
-        s_v[1][r][c] = t1;
-        s_v[2][r][c] = t2;
     }
     __syncthreads();
 
-    // horizontal pass
-    const int c = tid & (PE_TW - 1);
-    const int gx = x0 + c;
-    const long long plane = (long long)h * w;
+    // horizontal pass: one thread per (row, 4 adjacent outputs): 16 values of each moment row via LDS.128
+    const int plane = h * w;
     float4* dst_a = reinterpret_cast<float4*>(R + (long long)img * img_stride);
-    float* dst_b = R + (long long)img * img_stride + 4 * plane;
-    for (int r = tid >> 6; r < PE_TH; r += 4) {
+    float* dst_b = R + (long long)img * img_stride + 4 * (long long)plane;
+    constexpr int GROUPS = PE_SW / 4 - 2;     // 30 groups of 4 output columns (the last one is partly beyond PE_TW)
+    for (int task = tid; task < PE_TH * GROUPS; task += 256) {
+        const int r = task / GROUPS, cgp = task - r * GROUPS;
+        const int c0 = 4 * cgp;               // first output column (tile-relative); its region column is c0 + PE_N
         const int gy = y0 + r;
-        if (gx >= w || gy >= h) continue;
-        const float* v0 = &s_v[0][r][c + PE_N];
-        const float* v1 = &s_v[1][r][c + PE_N];
-        const float* v2 = &s_v[2][r][c + PE_N];
-        float b1 = v0[0] * pc.g[0], b2 = 0.f, b3 = v1[0] * pc.g[0], b4 = 0.f, b5 = v2[0] * pc.g[0], b6 = 0.f;
+        if (gy >= h || x0 + c0 >= w) continue;
+        float v0[16], v1[16], v2[16];         // region columns c0 .. c0+15  (outputs need c0 .. c0+13)
 #pragma unroll
-        for (int k = 1; k <= PE_N; ++k) {
-            const float tg = v0[k] + v0[-k];
-            b1 += tg * pc.g[k];
-            b4 += tg * pc.xxg[k];
-            b2 += (v0[k] - v0[-k]) * pc.xg[k];
-            b3 += (v1[k] + v1[-k]) * pc.g[k];
-            b6 += (v1[k] - v1[-k]) * pc.xg[k];
-            b5 += (v2[k] + v2[-k]) * pc.g[k];
+        for (int q = 0; q < 4; ++q) {
+            const float4 a = *reinterpret_cast<const float4*>(&s_v[0][r][c0 + 4 * q]);
+            const float4 b = *reinterpret_cast<const float4*>(&s_v[1][r][c0 + 4 * q]);
+            const float4 d = *reinterpret_cast<const float4*>(&s_v[2][r][c0 + 4 * q]);
+            v0[4 * q] = a.x; v0[4 * q + 1] = a.y; v0[4 * q + 2] = a.z; v0[4 * q + 3] = a.w;
+            v1[4 * q] = b.x; v1[4 * q + 1] = b.y; v1[4 * q + 2] = b.z; v1[4 * q + 3] = b.w;
+            v2[4 * q] = d.x; v2[4 * q + 1] = d.y; v2[4 * q + 2] = d.z; v2[4 * q + 3] = d.w;
         }
-        const long long o = (long long)gy * w + gx;
-        dst_a[o] = make_float4(b3 * pc.ig11, b2 * pc.ig11, b1 * pc.ig03 + b5 * pc.ig33, b1 * pc.ig03 + b4 * pc.ig33);
-        dst_b[o] = b6 * pc.ig55;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gx = x0 + c0 + i;
+            if (c0 + i >= PE_TW || gx >= w) continue;
+            const int m = i + PE_N;           // index of the output's own column in v*
+            float b1 = v0[m] * pc.g[0], b2 = 0.f, b3 = v1[m] * pc.g[0], b4 = 0.f, b5 = v2[m] * pc.g[0], b6 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= PE_N; ++k) {
+                const float tg = v0[m + k] + v0[m - k];
+                b1 += tg * pc.g[k];
+                b4 += tg * pc.xxg[k];
+                b2 += (v0[m + k] - v0[m - k]) * pc.xg[k];
+                b3 += (v1[m + k] + v1[m - k]) * pc.g[k];
+                b6 += (v1[m + k] - v1[m - k]) * pc.xg[k];
+                b5 += (v2[m + k] + v2[m - k]) * pc.g[k];
+            }
+            const int o = gy * w + gx;
+            dst_a[o] = make_float4(b3 * pc.ig11, b2 * pc.ig11, b1 * pc.ig03 + b5 * pc.ig33, b1 * pc.ig03 + b4 * pc.ig33);
+            dst_b[o] = b6 * pc.ig55;
+        }
     }
 }
 
 int launch_polyexp(const float* I, float* R, long long img_stride, int n_img, int h, int w, const PolyConsts& pc,
                    cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(polyexp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM_BYTES);
+        attr_set = true;
+    }
     LaunchTimer lt(KC_POLYEXP, 24.0 * h * w * n_img, s, cdiv(n_img, 65535));
     for (int z0 = 0; z0 < n_img; z0 += 65535) {
         const int nz = min(n_img - z0, 65535);
         dim3 g(cdiv(w, PE_TW), cdiv(h, PE_TH), nz);
-        polyexp_kernel<<<g, 256, 0, s>>>(I + (long long)z0 * h * w, R + (long long)z0 * img_stride, img_stride, h, w, pc);
+        polyexp_kernel<<<g, 256, PE_SMEM_BYTES, s>>>(I + (long long)z0 * h * w, R + (long long)z0 * img_stride, img_stride, h,
+                                                     w, pc);
     }
     return check_launch("polyexp");
 }

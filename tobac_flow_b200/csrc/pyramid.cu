@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(256) blur_v4_kernel(const uint8_t* __restrict_
     const int rad = taps.ksize >> 1;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool interior = sy - rad >= 0 && sy + rad < H;
+#pragma unroll 4
     for (int k = 0; k < taps.ksize; ++k) {
         const int yy = interior ? sy + k - rad : reflect101(sy + k - rad, H);
         const uchar4 c = __ldg(src + yy * W4 + x4);
@@ -144,13 +145,31 @@ __global__ void __launch_bounds__(256) blur_h_resize_kernel(const float* __restr
         const float* row0 = rows;
         const float* row1 = rp == 2 ? rows + W : rows;
         float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
-        for (int k = 0; k < taps.ksize; ++k) {
-            const float wk = taps.w[k];
-            const int xa = reflect101(x0 + k - rad, W), xb = reflect101(x1 + k - rad, W);
-            b00 += wk * row0[xa];
-            b01 += wk * row0[xb];
-            b10 += wk * row1[xa];
-            b11 += wk * row1[xb];
+        if (x1 == x0 + 1 && x0 - rad >= 0 && x1 + rad < W) {
+            // interior: the two column positions are neighbours, so one pass over ksize+1 values feeds both
+            const float* p0 = row0 + x0 - rad;
+            const float* p1 = row1 + x0 - rad;
+            float a0 = p0[0], a1 = p1[0];
+#pragma unroll 4
+            for (int k = 0; k < taps.ksize; ++k) {
+                const float wk = taps.w[k];
+                const float n0 = p0[k + 1], n1 = p1[k + 1];
+                b00 += wk * a0;
+                b01 += wk * n0;
+                b10 += wk * a1;
+                b11 += wk * n1;
+                a0 = n0;
+                a1 = n1;
+            }
+        } else {
+            for (int k = 0; k < taps.ksize; ++k) {
+                const float wk = taps.w[k];
+                const int xa = reflect101(x0 + k - rad, W), xb = reflect101(x1 + k - rad, W);
+                b00 += wk * row0[xa];
+                b01 += wk * row0[xb];
+                b10 += wk * row1[xa];
+                b11 += wk * row1[xb];
+            }
         }
         const float r0 = b00 * (1.f - fx) + b01 * fx;
         const float r1 = b10 * (1.f - fx) + b11 * fx;
