@@ -103,6 +103,32 @@ int tf_farneback_pairs(const uint8_t* q0, const uint8_t* q1, float* fwd, long lo
                        long long bwd_stride, int n_pairs, int H, int W, const tf_fb_params* p /* host */,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* cv2.VariationalRefinement parameters; tf_vr_default_params() gives cv2.VariationalRefinement.create()'s defaults
+ * (the module-level vr_model of tobac_flow/flow.py:359). */
+typedef struct tf_vr_params {
+    float alpha;                 /* 20   smoothness weight */
+    float delta;                 /* 5    brightness-constancy weight */
+    float gamma;                 /* 10   gradient-constancy weight */
+    float omega;                 /* 1.6  SOR relaxation */
+    int fixed_point_iterations;  /* 5 */
+    int sor_iterations;          /* 5 */
+    float zeta;                  /* 0.1 */
+    float epsilon;               /* 0.001 */
+} tf_vr_params;
+
+void tf_vr_default_params(tf_vr_params* p /* host */);
+size_t tf_vr_workspace_bytes(int n_pairs, int H, int W);
+
+/*
+ * Variational refinement of the forward and backward flow of n_pairs quantised pairs, in place.
+ * Replaces vr_model.calc(prev, next, forward_flow) and vr_model.calc(next, prev, backward_flow)
+ * (tobac_flow/flow.py:513-519, taken when vr_steps > 0; cv2.VariationalRefinement::calc).
+ * Same pair addressing as tf_farneback_pairs.
+ */
+int tf_variational_refinement(const uint8_t* q0, const uint8_t* q1, float* fwd, long long fwd_stride, float* bwd,
+                              long long bwd_stride, int n_pairs, int H, int W, const tf_vr_params* p /* host */,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /*
  * One smooth_flow_step (tobac_flow/flow.py:530-568) on n_pairs (fwd, bwd) fields in place semantics:
  * fwd' = nanmean(fwd, -warp(bwd by fwd)), bwd' = nanmean(bwd, -warp(fwd by bwd)), both from the old
@@ -145,7 +171,8 @@ int tf_sl_convolve(const void* cur0, int n_frames, int has_prev, int has_next, c
 /*
  * Launch accounting (used by bench.py; no reference counterpart).  Kernel classes:
  *   0 normalise, 1 pyramid, 2 polyexp, 3 flow upsample, 4 Farneback iteration (coarser levels),
- *   5 Farneback iteration at the full-resolution level, 6 semi-Lagrangian gather, 7 flow smoothing, 8 finalise.
+ *   5 Farneback iteration at the full-resolution level, 6 semi-Lagrangian gather, 7 flow smoothing, 8 finalise,
+ *   9 variational refinement.
  * Launch counts and algorithmic bytes are always accumulated; device time is measured with CUDA events recorded
  * on the launching stream while profiling is enabled.  tf_profile_read synchronises on the recorded events.
  */

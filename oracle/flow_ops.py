@@ -92,7 +92,16 @@ def smooth_flow_step(fwd, bwd, method="linear", backend="numpy"):
     return blend(fwd, bwd), blend(bwd, fwd)
 
 
-def calculate_flow(data, smoothing_passes=0, interp_method="linear", backend="numpy"):
+def refine_pair(q0, q1, fwd, bwd, backend="numpy"):
+    """flow.py:513-519: vr_model.calc(prev, next, fwd), vr_model.calc(next, prev, bwd)."""
+    if backend == "cv2":
+        vr = _cv2.VariationalRefinement_create()
+        return vr.calc(q0, q1, fwd.copy()), vr.calc(q1, q0, bwd.copy())
+    from . import varref_np
+    return varref_np.variational_refinement(q0, q1, fwd), varref_np.variational_refinement(q1, q0, bwd)
+
+
+def calculate_flow(data, smoothing_passes=0, interp_method="linear", backend="numpy", vr_steps=0):
     data = np.asarray(data)
     T = data.shape[0]
     fwd = np.full(data.shape + (2,), np.nan, dtype=F32)
@@ -100,6 +109,8 @@ def calculate_flow(data, smoothing_passes=0, interp_method="linear", backend="nu
     for i in range(T - 1):
         q0, q1 = pair_to_u8(data[i], data[i + 1])
         f, b = farneback_pair(q0, q1, backend)
+        if vr_steps > 0:
+            f, b = refine_pair(q0, q1, f, b, backend)
         for _ in range(smoothing_passes):
             f, b = smooth_flow_step(f, b, interp_method, backend)
         fwd[i], bwd[i + 1] = f, b
@@ -108,8 +119,8 @@ def calculate_flow(data, smoothing_passes=0, interp_method="linear", backend="nu
     return fwd, bwd
 
 
-def create_flow(data, smoothing_passes=0, interp_method="linear", max_value=20, backend="numpy"):
-    fwd, bwd = calculate_flow(data, smoothing_passes, interp_method, backend)
+def create_flow(data, smoothing_passes=0, interp_method="linear", max_value=20, backend="numpy", vr_steps=0):
+    fwd, bwd = calculate_flow(data, smoothing_passes, interp_method, backend, vr_steps)
     fwd = np.minimum(np.maximum(fwd, -max_value), max_value)
     bwd = np.minimum(np.maximum(bwd, -max_value), max_value)
     return fwd, bwd

@@ -49,6 +49,23 @@ def _cubic_coeffs(frac_idx: np.ndarray) -> np.ndarray:
     return np.stack([c0, c1, c2, c3], -1).astype(F32)
 
 
+def remap_linear_replicate(src: np.ndarray, mapx: np.ndarray, mapy: np.ndarray) -> np.ndarray:
+    """cv2.remap(src32f, map, INTER_LINEAR, BORDER_REPLICATE) (used by cv2.VariationalRefinement): same 1/32-px
+    quantisation and weights as below, taps clamped to the image."""
+    src = np.asarray(src, dtype=F32)
+    H, W = src.shape
+    sx = _round_half_even_i64(np.asarray(mapx, F32) * F32(32))
+    sy = _round_half_even_i64(np.asarray(mapy, F32) * F32(32))
+    ix, iy = _sat_short(sx >> 5), _sat_short(sy >> 5)
+    fx = ((sx & 31).astype(F32) * F32(1.0 / 32.0)).astype(F32)
+    fy = ((sy & 31).astype(F32) * F32(1.0 / 32.0)).astype(F32)
+    x0, x1 = np.clip(ix, 0, W - 1), np.clip(ix + 1, 0, W - 1)
+    y0, y1 = np.clip(iy, 0, H - 1), np.clip(iy + 1, 0, H - 1)
+    one = F32(1)
+    w00, w01, w10, w11 = (one - fy) * (one - fx), (one - fy) * fx, fy * (one - fx), fy * fx
+    return (((src[y0, x0] * w00 + src[y0, x1] * w01) + src[y1, x0] * w10) + src[y1, x1] * w11).astype(F32)
+
+
 def remap(src: np.ndarray, mapx: np.ndarray, mapy: np.ndarray, method: str = "linear",
           fill_value=np.nan) -> np.ndarray:
     """Gather ``src`` (H, W) at float32 positions (mapx, mapy) (any common shape)."""

@@ -122,6 +122,13 @@ def main():
     out["bwd_smooth1_cubic"] = fs.backward_flow
     np.savez_compressed(os.path.join(HERE, "bt_small.npz"), **out)
 
+    # ---- production flow settings of scripts/dcc_detect_goes.py:164-166 ------------------------------------
+    fp = create_flow(bt, model="Farneback", vr_steps=1, smoothing_passes=1, interp_method="cubic")
+    fv = create_flow(bt, vr_steps=1)
+    np.savez_compressed(os.path.join(HERE, "bt_small_production.npz"), meta=str(meta),
+                        fwd_vr1_smooth1_cubic=fp.forward_flow, bwd_vr1_smooth1_cubic=fp.backward_flow,
+                        fwd_vr1=fv.forward_flow, bwd_vr1=fv.backward_flow)
+
     # ---- three pyramid levels with half-even level sizes --------------------------------------
     bt3 = three_level()
     f3 = create_flow(bt3)
@@ -149,7 +156,7 @@ def main():
                         mask025=np.packbits(filtered >= 0.25), mask05=np.packbits(filtered >= 0.5), markers=markers.astype(np.int32),
                         n_markers=np.array(int(markers.max())))
     print("growth markers:", int(markers.max()), "marked px:", int((markers > 0).sum()))
-    for n in ("blob100", "bt_small", "three_level", "growth"):
+    for n in ("blob100", "bt_small", "bt_small_production", "three_level", "growth"):
         print(n, os.path.getsize(os.path.join(HERE, n + ".npz")) // 1024, "KiB")
 
 

@@ -352,3 +352,37 @@ def test_two_emulated_shards_equal_unsharded(tfb):
     # world == 1 goes through create_flow_sharded itself
     one = D.create_flow_sharded(D.make_shard(frames, 0, 1))
     assert np.array_equal(one.fwd.cpu().numpy(), full.forward_flow) and np.array_equal(one.bwd.cpu().numpy(), full.backward_flow)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# variational refinement (vr_steps > 0) and the production flow settings
+# ------------------------------------------------------------------------------------------------------------------
+def test_variational_refinement_vs_reference_golden(tfb, golden):
+    g = golden("bt_small_production")
+    bt = cases.small_bt()
+    f = tfb.create_flow(bt, vr_steps=1)
+    assert_flow_close(f.forward_flow, g["fwd_vr1"], 2e-3, 2e-2)
+    assert_flow_close(f.backward_flow, g["bwd_vr1"], 2e-3, 2e-2)
+    # the refinement must have changed the Farneback field
+    f0 = tfb.create_flow(bt)
+    assert np.abs(f.forward_flow - f0.forward_flow).max() > 0.05
+
+
+def test_production_settings_vs_reference_golden(tfb, golden):
+    """scripts/dcc_detect_goes.py:164-166: create_flow(bt, model="Farneback", vr_steps=1, smoothing_passes=1,
+    interp_method="cubic")."""
+    g = golden("bt_small_production")
+    f = tfb.create_flow(cases.small_bt(), model="Farneback", vr_steps=1, smoothing_passes=1, interp_method="cubic")
+    assert_flow_close(f.forward_flow, g["fwd_vr1_smooth1_cubic"], 2e-3, 2e-2)
+    assert_flow_close(f.backward_flow, g["bwd_vr1_smooth1_cubic"], 2e-3, 2e-2)
+    assert np.abs(f.forward_flow).max() <= 20
+
+
+@pytest.mark.parametrize("shape", [(33, 47), (100, 259)])
+def test_variational_refinement_vs_opencv(tfb, shape):
+    h, w = shape
+    bt = synthetic.bt_sequence(3, h, w, seed=h + w, nans=False)
+    f = tfb.create_flow(bt, vr_steps=1)
+    rf, rb = ops.create_flow(bt, vr_steps=1, backend="cv2" if ops.have_cv2() else "numpy")
+    assert_flow_close(f.forward_flow, rf, 2e-3, 2e-2)
+    assert_flow_close(f.backward_flow, rb, 2e-3, 2e-2)

@@ -21,10 +21,11 @@ EXPORTS = (
     "tf_version", "tf_last_error", "tf_fb_default_params", "tf_fb_level_plan", "tf_fb_poly_constants",
     "tf_farneback_workspace_bytes", "tf_pair_normalise_u8", "tf_farneback_pairs", "tf_smooth_flow_step",
     "tf_flow_finalise", "tf_sl_convolve", "tf_profile_enable", "tf_profile_reset", "tf_profile_read",
+    "tf_vr_default_params", "tf_vr_workspace_bytes", "tf_variational_refinement",
 )
 
 KERNEL_CLASSES = ("normalise", "pyramid", "polyexp", "flow_upsample", "fb_iter_coarse", "fb_iter_fullres",
-                  "sl_gather", "smooth_flow", "finalise")
+                  "sl_gather", "smooth_flow", "finalise", "variational_refinement")
 
 
 class FbParams(ctypes.Structure):
@@ -32,6 +33,14 @@ class FbParams(ctypes.Structure):
         ("num_levels", ctypes.c_int), ("pyr_scale", ctypes.c_double), ("win_size", ctypes.c_int),
         ("num_iters", ctypes.c_int), ("poly_n", ctypes.c_int), ("poly_sigma", ctypes.c_double),
         ("max_value", ctypes.c_float),
+    ]
+
+
+class VrParams(ctypes.Structure):
+    _fields_ = [
+        ("alpha", ctypes.c_float), ("delta", ctypes.c_float), ("gamma", ctypes.c_float), ("omega", ctypes.c_float),
+        ("fixed_point_iterations", ctypes.c_int), ("sor_iterations", ctypes.c_int), ("zeta", ctypes.c_float),
+        ("epsilon", ctypes.c_float),
     ]
 
 
@@ -68,6 +77,13 @@ def load():
     lib.tf_flow_finalise.argtypes = [vp, vp, ci, ci, ci, cf, ci, ci, ci, vp]
     lib.tf_sl_convolve.argtypes = [vp, ci, ci, ci, vp, vp, vp, ll, ci, ci, ci, ci, ci, ci,
                                    ctypes.POINTER(ctypes.c_uint8), cd, vp]
+    lib.tf_vr_default_params.argtypes = [ctypes.POINTER(VrParams)]
+    lib.tf_vr_default_params.restype = None
+    lib.tf_vr_workspace_bytes.argtypes = [ci, ci, ci]
+    lib.tf_vr_workspace_bytes.restype = ctypes.c_size_t
+    lib.tf_variational_refinement.argtypes = [vp, vp, vp, ll, vp, ll, ci, ci, ci, ctypes.POINTER(VrParams), vp,
+                                              ctypes.c_size_t, vp]
+    lib.tf_variational_refinement.restype = ci
     lib.tf_profile_enable.argtypes = [ci]
     lib.tf_profile_read.argtypes = [ci, ctypes.POINTER(cd), ctypes.POINTER(cd), ctypes.POINTER(ll)]
     for name in ("tf_profile_enable", "tf_profile_reset", "tf_profile_read", "tf_fb_level_plan", "tf_fb_poly_constants", "tf_pair_normalise_u8", "tf_farneback_pairs",
@@ -89,6 +105,12 @@ def default_params(max_value=20.0):
     p = FbParams()
     load().tf_fb_default_params(ctypes.byref(p))
     p.max_value = float(max_value) if max_value is not None else 0.0
+    return p
+
+
+def default_vr_params():
+    p = VrParams()
+    load().tf_vr_default_params(ctypes.byref(p))
     return p
 
 

@@ -28,9 +28,9 @@ def shard_bounds(T: int, world: int, rank: int):
 class CudaOps:
     """The product back-end: the CUDA kernels through the C ABI."""
 
-    def calculate_flow(self, frames, fwd, bwd, smoothing_passes, interp_method, max_value):
+    def calculate_flow(self, frames, fwd, bwd, smoothing_passes, interp_method, max_value, vr_steps=0):
         from .flow import calculate_flow_device
-        calculate_flow_device(frames, fwd, bwd, smoothing_passes, interp_method, max_value)
+        calculate_flow_device(frames, fwd, bwd, smoothing_passes, interp_method, max_value, vr_steps=vr_steps)
 
     def finalise(self, fwd, bwd, max_value, clamp_all, mirror_first, mirror_last):
         from .flow import finalise_flow_device
@@ -112,7 +112,7 @@ class ShardedFlow:
 
 
 def create_flow_sharded(shard: Shard, smoothing_passes=0, interp_method="linear", max_value=20, ops=None, group=None,
-                        exchange=True, fwd=None, bwd=None) -> ShardedFlow:
+                        exchange=True, fwd=None, bwd=None, vr_steps=0) -> ShardedFlow:
     """``create_flow`` for one rank of a time-sharded series; ``shard.buf[1:-1]`` holds the rank's frames."""
     ops = ops or CudaOps()
     rank, world = shard.rank, shard.world
@@ -126,7 +126,10 @@ def create_flow_sharded(shard: Shard, smoothing_passes=0, interp_method="linear"
         # one extra slot: backward_flow of the next rank's first frame, produced here, sent on below
         bwd = torch.full((T_loc + 1, H, W, 2), float("nan"), dtype=torch.float32, device=dev)
     frames = shard.buf[1:T_loc + 2] if shard.has_next else shard.buf[1:T_loc + 1]
-    ops.calculate_flow(frames, fwd, bwd, smoothing_passes, interp_method, max_value)
+    if vr_steps:
+        ops.calculate_flow(frames, fwd, bwd, smoothing_passes, interp_method, max_value, vr_steps=vr_steps)
+    else:
+        ops.calculate_flow(frames, fwd, bwd, smoothing_passes, interp_method, max_value)
     if world > 1:
         p2p = []
         if shard.has_next:
@@ -134,6 +137,6 @@ def create_flow_sharded(shard: Shard, smoothing_passes=0, interp_method="linear"
         if shard.has_prev:
             p2p.append(dist.P2POp(dist.irecv, bwd[0], rank - 1, group))
         _p2p(p2p, group)
-    clamp_all = max_value is not None and smoothing_passes > 0
+    clamp_all = max_value is not None and (smoothing_passes > 0 or bool(vr_steps))
     ops.finalise(fwd, bwd[:T_loc], max_value, clamp_all, rank == 0, rank == world - 1)
     return ShardedFlow(fwd, bwd[:T_loc], rank, world, ops, group)

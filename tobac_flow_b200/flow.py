@@ -397,13 +397,13 @@ def _check_model(model: str, vr_steps: int):
             "'DIS', 'DenseRLOF', 'DualTVL1'")
     if model != "Farneback":
         raise NotImplementedError(f"optical-flow model '{model}' is not built in tobac_flow_b200 (only 'Farneback')")
-    if vr_steps and vr_steps > 0:
-        raise NotImplementedError("variational refinement (vr_steps > 0) is not built in tobac_flow_b200 yet")
 
 
-def _pair_batch(n_pairs: int, H: int, W: int, params) -> int:
+def _pair_batch(n_pairs: int, H: int, W: int, params, vr: bool = False) -> int:
     """Pairs per launch batch: as many as fit comfortably in free HBM, capped so coarse levels still fill 148 SMs."""
     per_pair = _lib.workspace_bytes(1, H, W, params) + 2 * H * W
+    if vr:
+        per_pair += int(_lib.load().tf_vr_workspace_bytes(1, H, W))
     free, _ = torch.cuda.mem_get_info()
     by_mem = max(1, int(free * 0.6) // per_pair)
     by_px = max(1, (96 << 20) // (H * W))
@@ -412,7 +412,7 @@ def _pair_batch(n_pairs: int, H: int, W: int, params) -> int:
 
 def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Tensor, smoothing_passes: int = 0,
                           interp_method: str = "linear", max_value: float | None = None,
-                          next_frames: torch.Tensor | None = None, batch: int | None = None) -> None:
+                          next_frames: torch.Tensor | None = None, batch: int | None = None, vr_steps: int = 0) -> None:
     """Fill ``fwd[i]`` and ``bwd[i + 1]`` for every consecutive pair of ``frames`` (device tensors, in place).
 
     ``frames`` (T, H, W) float32; ``fwd``/``bwd`` (>= T, H, W, 2) float32.  With ``next_frames`` the pairs are
@@ -425,15 +425,22 @@ def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Te
     if n_pairs <= 0:
         return
     interp = _interp_code(interp_method)
-    fuse_clamp = (max_value is not None) and smoothing_passes == 0
+    use_vr = bool(vr_steps) and vr_steps > 0   # flow.py:513-519: one refinement whenever vr_steps > 0
+    fuse_clamp = (max_value is not None) and smoothing_passes == 0 and not use_vr
     params = _lib.default_params(max_value if fuse_clamp else 0.0)
-    nb = batch or _pair_batch(n_pairs, H, W, params)
+    nb = batch or _pair_batch(n_pairs, H, W, params, use_vr)
     dev = frames.device
     q0 = torch.empty((nb, H, W), dtype=torch.uint8, device=dev)
     q1 = torch.empty((nb, H, W), dtype=torch.uint8, device=dev)
     mm = torch.empty((2 * nb,), dtype=torch.float32, device=dev)
     ws_bytes = _lib.workspace_bytes(nb, H, W, params)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    vr_params = vr_ws = None
+    vr_bytes = 0
+    if use_vr:
+        vr_params = _lib.default_vr_params()
+        vr_bytes = int(lib.tf_vr_workspace_bytes(nb, H, W))
+        vr_ws = torch.empty((vr_bytes,), dtype=torch.uint8, device=dev)
     tmp_f = tmp_b = None
     if smoothing_passes > 0:
         tmp_f = torch.empty((nb, H, W, 2), dtype=torch.float32, device=dev)
@@ -451,6 +458,10 @@ def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Te
         bo = bwd.data_ptr() + (p0 + 1) * hw * 2 * 4
         _lib.check(lib.tf_farneback_pairs(q0.data_ptr(), q1.data_ptr(), fo, hw * 2, bo, hw * 2, n, H, W,
                                           ctypes.byref(params), ws.data_ptr(), ws_bytes, st), "tf_farneback_pairs")
+        if use_vr:
+            _lib.check(lib.tf_variational_refinement(q0.data_ptr(), q1.data_ptr(), fo, hw * 2, bo, hw * 2, n, H, W,
+                                                     ctypes.byref(vr_params), vr_ws.data_ptr(), vr_bytes, st),
+                       "tf_variational_refinement")
         for _ in range(smoothing_passes):
             _lib.check(lib.tf_smooth_flow_step(fo, bo, tmp_f.data_ptr(), tmp_b.data_ptr(), hw * 2, n, H, W, interp, st),
                        "tf_smooth_flow_step")
@@ -488,12 +499,12 @@ def _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_meth
     fwd = torch.full((T, H, W, 2), float("nan"), dtype=torch.float32, device=frames.device)
     bwd = torch.full((T, H, W, 2), float("nan"), dtype=torch.float32, device=frames.device)
     if frames_b is None:
-        calculate_flow_device(frames, fwd, bwd, smoothing_passes, interp_method, max_value)
+        calculate_flow_device(frames, fwd, bwd, smoothing_passes, interp_method, max_value, vr_steps=vr_steps)
     else:
         # calculate_flow_2 (flow.py:431-496): pairs (a[i], b[i]) for i < T-1
         calculate_flow_device(frames[:T - 1], fwd, bwd, smoothing_passes, interp_method, max_value,
-                              next_frames=frames_b[:T - 1])
-    clamp_all = max_value is not None and smoothing_passes > 0
+                              next_frames=frames_b[:T - 1], vr_steps=vr_steps)
+    clamp_all = max_value is not None and (smoothing_passes > 0 or (bool(vr_steps) and vr_steps > 0))
     finalise_flow_device(fwd, bwd, max_value, clamp_all)
     return fwd, bwd
 
