@@ -496,8 +496,14 @@ def _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_meth
     if data_b is not None:
         frames_b, _ = _to_device(data_b, torch.float32)
     T, H, W = frames.shape
-    fwd = torch.full((T, H, W, 2), float("nan"), dtype=torch.float32, device=frames.device)
-    bwd = torch.full((T, H, W, 2), float("nan"), dtype=torch.float32, device=frames.device)
+    # the reference pre-fills with NaN (flow.py:408-409); for T > 1 every element is overwritten (pairs + end
+    # rules), so the fill is only materialised for the degenerate single-frame case
+    if T > 1:
+        fwd = torch.empty((T, H, W, 2), dtype=torch.float32, device=frames.device)
+        bwd = torch.empty((T, H, W, 2), dtype=torch.float32, device=frames.device)
+    else:
+        fwd = torch.full((T, H, W, 2), float("nan"), dtype=torch.float32, device=frames.device)
+        bwd = torch.full((T, H, W, 2), float("nan"), dtype=torch.float32, device=frames.device)
     if frames_b is None:
         calculate_flow_device(frames, fwd, bwd, smoothing_passes, interp_method, max_value, vr_steps=vr_steps)
     else:
