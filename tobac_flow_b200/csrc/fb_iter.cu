@@ -9,9 +9,9 @@
 //   * M phase, one thread per column, software-pipelined one row ahead (the next row's gathers and the flow of the
 //     row after that are in flight while the current row is computed): flow (8 B), R0 (float4 + float) and the
 //     bilinear R1 gather at p + flow (4 x (float4 + float)) -> the five M terms.  Rows are handled in batches of 4;
-//     the vertical 13-row window sum is assembled from fresh partial sums (suffix of batch b-3 kept in a small
-//     shared-memory ring, the full sums of batches b-2 and b-1 in registers, the running prefix of batch b), so
-//     rounding never accumulates down the chunk;
+//     the vertical 13-row window sum is assembled from fresh partial sums (prefix sums of batch b-3 kept in a small
+//     shared-memory ring and subtracted from its full sum, the full sums of batches b-3..b-1 in registers, the
+//     running prefix of batch b), so rounding never accumulates down the chunk;
 //   * H phase, every 4 rows: the vertical sums of 4 rows are exchanged through shared memory; each thread takes one row
 //     and 4 adjacent outputs, slides the horizontal 13-column window over them, solves the 2x2 systems in registers and
 //     stores the new flow (32 B per thread, coalesced).
