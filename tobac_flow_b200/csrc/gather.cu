@@ -338,27 +338,38 @@ __global__ void __launch_bounds__(256) sl_gather_kernel(GatherArgs a) {
         if (!bits) continue;
         const float2 f = slab == 0 ? bf : ff;
         const FrameSrc<SrcT>& src = slab == 0 ? prev : next;
-        SrcT patch[9];
-        bool have_patch = false;
-        if constexpr (INTERP == TF_LINEAR && !std::is_same<SrcT, int>::value) {
-            if (slab != 1 && bits == 0x1ffu && src.p != nullptr) have_patch = linear_patch9<SrcT>(src.p, H, W, f, x, y, patch);
+        // the (up to) nine tap values of this slab, gathered first so that the patch / per-tap choice is one branch
+        SrcT tapv[9];
+        bool oob1[9];
+        if (slab == 1) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                if (!((bits >> j) & 1u)) continue;
+                const int yy = y + j / 3 - 1, xx = x + j % 3 - 1;
+                oob1[j] = !((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W);
+                tapv[j] = oob1[j] ? fill_s : cur[yy * W + xx];
+            }
+        } else {
+            bool have_patch = false;
+            if constexpr (INTERP == TF_LINEAR && !std::is_same<SrcT, int>::value) {
+                if (bits == 0x1ffu && src.p != nullptr) have_patch = linear_patch9<SrcT>(src.p, H, W, f, x, y, tapv);
+            }
+            if (!have_patch) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    if (!((bits >> j) & 1u)) continue;
+                    // p = fl32(fl32(flow + offset) + grid)   (convolve.py:56-63)
+                    const float px = __fadd_rn(__fadd_rn(f.x, (float)(j % 3 - 1)), (float)x);
+                    const float py = __fadd_rn(__fadd_rn(f.y, (float)(j / 3 - 1)), (float)y);
+                    tapv[j] = remap_at<INTERP, SrcT>(src, px, py);
+                }
+            }
         }
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
             if (!((bits >> j) & 1u)) continue;
-            const int dy = j / 3 - 1, dx = j % 3 - 1;
-            ST v;
-            if (slab == 1) {
-                const int yy = y + dy, xx = x + dx;
-                v = ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) ? cast_to<SrcT, ST>(cur[yy * W + xx]) : fill_st;
-            } else if (have_patch) {
-                v = cast_to<SrcT, ST>(patch[j]);
-            } else {
-                // p = fl32(fl32(flow + offset) + grid)   (convolve.py:56-63)
-                const float px = __fadd_rn(__fadd_rn(f.x, (float)dx), (float)x);
-                const float py = __fadd_rn(__fadd_rn(f.y, (float)dy), (float)y);
-                v = cast_to<SrcT, ST>(remap_at<INTERP, SrcT>(src, px, py));
-            }
+            // same-step taps outside the image take the fill value in the STACK dtype (convolve.py:140-142)
+            const ST v = (slab == 1 && oob1[j]) ? fill_st : cast_to<SrcT, ST>(tapv[j]);
             const int k = slab * 9 + j;
             if (RC == RC_NONE) rn.add(n, k, v);
             if (RC == RC_DIFF) rd.add(n, k, v);
