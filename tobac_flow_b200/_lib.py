@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtobacflow_b200.so")
+# TF_LIB_PATH: load an alternative build of the same library (kernel A/B experiments)
+LIB_PATH = os.environ.get("TF_LIB_PATH") or os.path.join(HERE, "libtobacflow_b200.so")
 
 TF_F32, TF_F64, TF_I32 = 0, 1, 2
 TF_NEAREST, TF_LINEAR, TF_CUBIC = 0, 1, 2

@@ -57,6 +57,11 @@ __global__ void __launch_bounds__(256) blur_v_kernel(const uint8_t* __restrict__
     tmp[((long long)img * (h * rp) + r) * W + x] = acc;
 }
 
+// exact u8 -> fp32 without the quarter-rate I2F: splice the byte into the mantissa of 2^23 and subtract 2^23
+__device__ __forceinline__ float byte_to_float(unsigned v, unsigned sel) {
+    return __uint_as_float(__byte_perm(v, 0x4B000000u, sel)) - 8388608.f;
+}
+
 // pass A, 4 columns per thread (W % 4 == 0): one 32-bit load per tap row, float4 store
 __global__ void __launch_bounds__(256) blur_v4_kernel(const uint8_t* __restrict__ q0, const uint8_t* __restrict__ q1,
                                                       float* __restrict__ tmp, int H, int W, int h, int rp,
@@ -66,7 +71,7 @@ __global__ void __launch_bounds__(256) blur_v4_kernel(const uint8_t* __restrict_
     const int img = blockIdx.z;
     const int W4 = W >> 2;
     if (x4 >= W4) return;
-    const uchar4* src = reinterpret_cast<const uchar4*>(((img & 1) ? q1 : q0) + (long long)(img >> 1) * H * W);
+    const unsigned* src = reinterpret_cast<const unsigned*>(((img & 1) ? q1 : q0) + (long long)(img >> 1) * H * W);
     int sy;
     if (rp == 1) {
         sy = r;
@@ -81,12 +86,12 @@ __global__ void __launch_bounds__(256) blur_v4_kernel(const uint8_t* __restrict_
 #pragma unroll 4
     for (int k = 0; k < taps.ksize; ++k) {
         const int yy = interior ? sy + k - rad : reflect101(sy + k - rad, H);
-        const uchar4 c = __ldg(src + yy * W4 + x4);
+        const unsigned c = __ldg(src + yy * W4 + x4);
         const float wk = taps.w[k];
-        acc.x += wk * (float)c.x;
-        acc.y += wk * (float)c.y;
-        acc.z += wk * (float)c.z;
-        acc.w += wk * (float)c.w;
+        acc.x += wk * byte_to_float(c, 0x7540u);
+        acc.y += wk * byte_to_float(c, 0x7541u);
+        acc.z += wk * byte_to_float(c, 0x7542u);
+        acc.w += wk * byte_to_float(c, 0x7543u);
     }
     reinterpret_cast<float4*>(tmp + ((long long)img * (h * rp) + r) * W)[x4] = acc;
 }
