@@ -93,6 +93,19 @@ def _to_host(t: torch.Tensor) -> np.ndarray:
     return h.numpy()
 
 
+_HOST_CHUNK_BYTES = 192 << 20     # result bytes per pipelined chunk of the host path
+_HOST_PAIR_BATCH = 8              # pairs per launch batch while a host operand is still being uploaded
+_SIDE_STREAMS = {}
+
+
+def _side_streams(dev):
+    """(upload, download) copy streams of a device, created once."""
+    key = (dev.type, dev.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    return _SIDE_STREAMS[key]
+
+
 def _dtype_code(np_dtype):
     """``dtype=`` of the reference (a numpy dtype or None -> float64, np.full semantics) -> (torch dtype, code)."""
     dt = np.dtype(np.float64 if np_dtype is None else np_dtype)
@@ -308,14 +321,77 @@ class Flow:
         assert structure.shape == (3, 3, 3), "Structure input must be a 3x3x3 array"
         _interp_code(method)
         n_taps = int(np.count_nonzero(structure))
-        t, from_host = _to_device(data)
         reducer = recognise_reducer(func, n_taps, dtype)
+        if reducer is not None and not isinstance(data, torch.Tensor):
+            return self._convolve_host_pipelined(_as_numpy(data), structure, method, fill_value, dtype, reducer, n_taps)
+        t, from_host = _to_device(data)
         if reducer is None:
             res = self._convolve_python_func(t, structure, method, fill_value, dtype, func)
         else:
             res = convolve_device(t, self.forward_flow_device, self.backward_flow_device, structure, method,
                                   fill_value, dtype, reducer)
         return _to_host(res) if from_host else res
+
+    def _convolve_host_pipelined(self, a: np.ndarray, structure, method, fill_value, dtype, reducer, n_taps):
+        """Host operand -> host result with the PCIe copies overlapped with the kernels: the operand is uploaded in
+        time chunks on one side stream, each chunk is computed as soon as its one-frame halo has arrived, and its
+        result is copied into page-locked host memory on a second side stream while the next chunk computes."""
+        dev = _device()
+        a = np.ascontiguousarray(a)
+        if a.dtype == np.bool_ or (a.dtype.kind in "iu" and a.dtype != np.int32):
+            a = a.astype(np.int32)          # cv2's binding narrows wider integers the same way
+        elif a.dtype == np.float16:
+            a = a.astype(np.float32)
+        elif a.dtype not in (np.float32, np.float64, np.int32):
+            raise NotImplementedError(f"operand dtype {a.dtype} is not supported")
+        src = torch.from_numpy(a)
+        T, H, W = src.shape
+        out_t, _ = _dtype_code(dtype)
+        stack = reducer == _lib.TF_RED_NONE
+        host = torch.empty((n_taps, T, H, W) if stack else (T, H, W), dtype=out_t, pin_memory=True)
+        if T == 0:
+            return host.numpy()
+        fwd, bwd = self.forward_flow_device, self.backward_flow_device
+        per_frame = H * W * out_t.itemsize * (n_taps if stack else 1)
+        Tc = max(1, min(T, _HOST_CHUNK_BYTES // max(per_frame, 1)))
+        chunks = [(a0, min(a0 + Tc, T)) for a0 in range(0, T, Tc)]
+        cur = torch.cuda.current_stream()
+        s_in, s_out = _side_streams(dev)
+        d_in = torch.empty((T, H, W), dtype=src.dtype, device=dev)
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        ev_in = []
+        with torch.cuda.stream(s_in):
+            for a0, b0 in chunks:
+                d_in[a0:b0].copy_(src[a0:b0], non_blocking=True)
+                ev_in.append(torch.cuda.Event())
+                ev_in[-1].record(s_in)
+        bufs, ev_free = [None, None], [None, None]
+        for k, (a0, b0) in enumerate(chunks):
+            cur.wait_event(ev_in[min(k + 1, len(chunks) - 1)])      # this chunk and its right halo frame are here
+            slot = k & 1
+            if ev_free[slot] is not None:
+                cur.wait_event(ev_free[slot])                       # the buffer's previous contents are on the host
+            n = b0 - a0
+            shape = (n_taps, n, H, W) if stack else (n, H, W)
+            if bufs[slot] is None or tuple(bufs[slot].shape) != shape:
+                bufs[slot] = torch.empty(shape, dtype=out_t, device=dev)
+            convolve_device(d_in[max(a0 - 1, 0):min(b0 + 1, T)], fwd[a0:b0], bwd[a0:b0], structure, method, fill_value,
+                            dtype, reducer, has_prev=a0 > 0, has_next=b0 < T, out=bufs[slot])
+            ev_c = torch.cuda.Event()
+            ev_c.record(cur)
+            s_out.wait_event(ev_c)
+            with torch.cuda.stream(s_out):
+                if stack:
+                    for tap in range(n_taps):
+                        host[tap, a0:b0].copy_(bufs[slot][tap], non_blocking=True)
+                else:
+                    host[a0:b0].copy_(bufs[slot], non_blocking=True)
+                ev_free[slot] = torch.cuda.Event()
+                ev_free[slot].record(s_out)
+        s_out.synchronize()
+        cur.wait_stream(s_in)
+        return host.numpy()
 
     def _convolve_python_func(self, t, structure, method, fill_value, dtype, func):
         """Compatibility path for arbitrary Python reducers: the tap stack of each step is gathered by the
@@ -412,7 +488,8 @@ def _pair_batch(n_pairs: int, H: int, W: int, params, vr: bool = False) -> int:
 
 def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Tensor, smoothing_passes: int = 0,
                           interp_method: str = "linear", max_value: float | None = None,
-                          next_frames: torch.Tensor | None = None, batch: int | None = None, vr_steps: int = 0) -> None:
+                          next_frames: torch.Tensor | None = None, batch: int | None = None, vr_steps: int = 0,
+                          frames_ready: Callable | None = None) -> None:
     """Fill ``fwd[i]`` and ``bwd[i + 1]`` for every consecutive pair of ``frames`` (device tensors, in place).
 
     ``frames`` (T, H, W) float32; ``fwd``/``bwd`` (>= T, H, W, 2) float32.  With ``next_frames`` the pairs are
@@ -450,6 +527,8 @@ def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Te
     st = _stream()
     for p0 in range(0, n_pairs, nb):
         n = min(nb, n_pairs - p0)
+        if frames_ready is not None:
+            frames_ready(p0 + n)          # make the stream wait until frames [0, p0 + n] have been uploaded
         f0 = frames.data_ptr() + p0 * hw * es
         f1 = (frames.data_ptr() + (p0 + 1) * hw * es) if next_frames is None else (next_frames.data_ptr() + p0 * hw * es)
         _lib.check(lib.tf_pair_normalise_u8(f0, f1, hw, q0.data_ptr(), q1.data_ptr(), n, H, W, mm.data_ptr(), st),
@@ -489,7 +568,27 @@ def _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_meth
     _check_model(model, vr_steps)
     _select_normalisation(normalisation_method)
     _interp_code(interp_method)
-    frames, _ = _to_device(data, torch.float32)
+    frames_ready = batch = None
+    host_a = None if isinstance(data, torch.Tensor) else _as_numpy(data)
+    if host_a is not None and data_b is None and host_a.ndim == 3 and host_a.dtype == np.float32 and host_a.shape[0] > 2 * _HOST_PAIR_BATCH:
+        # host input: upload in chunks on a side stream and start on the first pairs while the rest is in flight
+        dev = _device()
+        src = torch.from_numpy(np.ascontiguousarray(host_a))
+        frames = torch.empty(tuple(src.shape), dtype=torch.float32, device=dev)
+        s_in, _ = _side_streams(dev)
+        s_in.wait_stream(torch.cuda.current_stream())
+        events = []
+        with torch.cuda.stream(s_in):
+            for a0 in range(0, src.shape[0], _HOST_PAIR_BATCH):
+                frames[a0:a0 + _HOST_PAIR_BATCH].copy_(src[a0:a0 + _HOST_PAIR_BATCH], non_blocking=True)
+                events.append(torch.cuda.Event())
+                events[-1].record(s_in)
+
+        def frames_ready(last_frame):
+            torch.cuda.current_stream().wait_event(events[min(last_frame // _HOST_PAIR_BATCH, len(events) - 1)])
+        batch = _HOST_PAIR_BATCH
+    else:
+        frames, _ = _to_device(data, torch.float32)
     if frames.dim() != 3:
         raise ValueError("data must have shape (t, y, x)")
     frames_b = None
@@ -505,7 +604,8 @@ def _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_meth
         fwd = torch.full((T, H, W, 2), float("nan"), dtype=torch.float32, device=frames.device)
         bwd = torch.full((T, H, W, 2), float("nan"), dtype=torch.float32, device=frames.device)
     if frames_b is None:
-        calculate_flow_device(frames, fwd, bwd, smoothing_passes, interp_method, max_value, vr_steps=vr_steps)
+        calculate_flow_device(frames, fwd, bwd, smoothing_passes, interp_method, max_value, vr_steps=vr_steps,
+                              batch=batch, frames_ready=frames_ready)
     else:
         # calculate_flow_2 (flow.py:431-496): pairs (a[i], b[i]) for i < T-1
         calculate_flow_device(frames[:T - 1], fwd, bwd, smoothing_passes, interp_method, max_value,
