@@ -168,11 +168,99 @@ int tf_sl_convolve(const void* cur0, int n_frames, int has_prev, int has_next, c
                    int stack_dtype, int interp, int reducer, const uint8_t* structure27 /* host */,
                    double fill, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * "Next" rows of the hot path: the per-frame filters of
+ * detect_growth_markers and the semi-Lagrangian labelling, so the pipeline stays on the device between Flow operators.
+ * Masks are uint8 (non-zero = True), one byte per pixel.
+ * --------------------------------------------------------------------------------------------------------------- */
+
+/* Bytes of scratch tf_flat_label / tf_binary_fill_holes need for a (T, H, W) stack. */
+size_t tf_ccl_workspace_bytes(int T, int H, int W);
+
+/*
+ * flat_label (tobac_flow/utils/label_utils.py:143-180 -> scipy.ndimage.label with the time links of the structure
+ * removed): 2-D connected components of every frame; numbering identical to scipy's (raster order of each component's
+ * first pixel, continuing across frames).  connectivity 1 = cross, 2 = full 3x3 (the middle slab of `structure`).
+ * labels: (T, H, W) int32 out; n_labels: device int32, may be NULL.
+ */
+int tf_flat_label(const uint8_t* mask, int32_t* labels, int T, int H, int W, int connectivity, int32_t* n_labels,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* scipy.ndimage.binary_fill_holes(mask, structure = 2-D cross per frame)  (tobac_flow/detection.py:72-87, 330-346). */
+int tf_binary_fill_holes(const uint8_t* mask, uint8_t* out, int T, int H, int W, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/*
+ * scipy.ndimage.gaussian_filter(field, (0, sigma, sigma)) (detection.py:65, 149): correlate1d along y then x, 'reflect'
+ * borders, fp64 accumulation in scipy's order, intermediate stored in the array dtype.  `weights` is the HOST array of
+ * 2*radius+1 kernel weights exactly as scipy.ndimage._filters._gaussian_kernel1d(sigma, 0, radius) returns them.
+ * in/tmp/out: (T, H, W) of `dtype` (TF_F32 or TF_F64); tmp may not alias in or out.
+ */
+int tf_gaussian_filter_yx(const void* in, void* tmp, void* out, int dtype, int T, int H, int W,
+                          const double* weights /* host */, int radius, void* stream);
+
+/* The curvature test of get_curvature_filter (detection.py:66-70, 77, 85): second differences along x and y (zero on
+ * the border), out = both < -threshold ("negative") or both > threshold (positive != 0). */
+int tf_curvature_mask(const void* smoothed, uint8_t* out, int dtype, int T, int H, int W, double threshold, int positive,
+                      void* stream);
+
+/* scipy.ndimage.binary_opening(mask, structure = 2-D cross per frame)  (detection.py:75, 111, 234, 289). */
+int tf_binary_opening_cross(const uint8_t* in, uint8_t* out, int T, int H, int W, void* stream);
+
+/* scipy.ndimage.grey_opening(field, footprint = 2-D cross per frame)  (detection.py:105-107), 'reflect' borders and
+ * scipy's NaN behaviour.  tmp: same shape/dtype, distinct from in and out. */
+int tf_grey_opening_cross(const void* in, void* tmp, void* out, int dtype, int T, int H, int W, void* stream);
+
+/* out[t] = (double)in[t] / dt[t]: Flow.diff(x) / get_time_diff_from_coord(x.t)[:, None, None]  (detection.py:99-101).
+ * dt: device array of T doubles. */
+int tf_scale_frames(const float* in, const double* dt, double* out, int T, int H, int W, void* stream);
+
+/* out = a * mask (a's dtype; NaN * 0 stays NaN as in numpy)  (detection.py:105-108). */
+int tf_mask_multiply(const void* a, const uint8_t* mask, void* out, int dtype, long long n, void* stream);
+
+/* out = (a >= threshold)  (detection.py:111, 115). */
+int tf_threshold_ge(const void* a, double threshold, uint8_t* out, int dtype, long long n, void* stream);
+
+/* max(flat) into the device int32 *out_max (the `bins.size - 1` of label.py:139 for arbitrary input labels). */
+int tf_label_max(const int32_t* flat, long long n, int32_t* out_max, void* stream);
+
+/*
+ * The overlap histogram of flow_label / flow_link_overlap (tobac_flow/label.py:139-163, 301-320;
+ * find_overlapping_labels, utils/label_utils.py:352-376) for all labels at once.
+ *   flat, back, fwd   n int32 each: the flat labels and the two outputs of
+ *                     Flow.convolve(flat, method="nearest", structure = time taps only)  (label.py:133-137)
+ *   sizes             out, n_labels+1 int32: np.bincount(flat)
+ *   keys, counts      out, open-addressing table of `capacity` (a power of two) entries: key = dir<<62 | L<<31 | M with
+ *                     dir 0 = forward, 1 = backward; empty slots keep key ~0
+ *   flags             out, 2 int32: [0] table overflow (retry with a larger capacity), [1] a label outside 0..n_labels
+ */
+int tf_label_overlap_count(const int32_t* flat, const int32_t* back, const int32_t* fwd, long long n, int32_t* sizes,
+                           int n_labels, unsigned long long* keys, int32_t* counts, long long capacity, int32_t* flags,
+                           void* stream);
+
+/* HOST function (all pointers host): the linking walk of label.py:139-163 over the table read back from
+ * tf_label_overlap_count, in the reference's visiting order.  map[l] = final label of flat label l.  Returns the
+ * number of linked objects, or a negative tf_status. */
+int tf_label_link_groups(const unsigned long long* keys, const int32_t* counts, long long capacity, const int32_t* sizes,
+                         int n_labels, double overlap, int absolute_overlap, int32_t* map);
+
+/*
+ * Per-label statistics for the marker filters of detect_growth_markers (tobac_flow/analysis.py:66-86:
+ * filter_labels_by_length -> time extent from ndi.find_objects, filter_labels_by_mask -> labeled_comprehension(np.any)).
+ * labels (T, hw) int32; mask_a / mask_b (T, hw) uint8 or NULL.  Outputs are device arrays of n_labels+1 int32:
+ * tmin / tmax = first / last frame of each label (tmax = -1 when absent), any_a / any_b = 1 if the label touches the mask.
+ */
+int tf_label_stats(const int32_t* labels, const uint8_t* mask_a, const uint8_t* mask_b, int T, long long hw, int n_labels,
+                   int32_t* tmin, int32_t* tmax, int32_t* any_a, int32_t* any_b, void* stream);
+
+/* out[i] = map[flat[i]]  (label.py:165-170); map is a device array of n_labels+1 int32. */
+int tf_relabel(const int32_t* flat, const int32_t* map, int32_t* out, long long n, int n_labels, void* stream);
+
 /*
  * Launch accounting (used by bench.py; no reference counterpart).  Kernel classes:
  *   0 normalise, 1 pyramid, 2 polyexp, 3 flow upsample, 4 Farneback iteration (coarser levels),
  *   5 Farneback iteration at the full-resolution level, 6 semi-Lagrangian gather, 7 flow smoothing, 8 finalise,
- *   9 variational refinement.
+ *   9 variational refinement, 10 labelling (flat_label, overlap graph, relabel), 11 detection filters.
  * Launch counts and algorithmic bytes are always accumulated; device time is measured with CUDA events recorded
  * on the launching stream while profiling is enabled.  tf_profile_read synchronises on the recorded events.
  */

@@ -57,6 +57,67 @@ def growth_case():
     return wvd.astype(np.float32)
 
 
+def growth_multi_case():
+    """14 x 120 x 160 wvd-like field with several cores: a long strong one, a short-lived one (dropped by the length
+    filter), a weak one (dropped by the >= 0.5 mask), a cold one (dropped by the wvd >= -5 mask) and two that merge."""
+    T, H, W = 14, 120, 160
+    base = synthetic.base_field(H, W, 123, sigma_px=10.0)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    #        y0  x0  t_start t_len depth  offset
+    cores = [(30, 30, 1, 9, 24.0, 0.0),      # strong, long
+             (30, 110, 4, 1, 6.0, 0.0),      # one-step jump: two frames above 0.25 -> dropped by the length filter
+             (85, 40, 2, 9, 16.0, 0.0),      # weak growth: never reaches 0.5
+             (90, 120, 1, 9, 30.0, -16.0),   # grows fast inside a cold patch: stays below -5
+             (60, 70, 2, 8, 22.0, 0.0),      # merges with the next one
+             (60, 84, 4, 8, 22.0, 0.0)]
+    wvd = np.empty((T, H, W), np.float32)
+    for t in range(T):
+        f = -25.0 + 5.0 * np.roll(base, (t, 2 * t), (0, 1))
+        for (y0, x0, ts, tl, depth, off) in cores:
+            g = float(np.clip((t - ts) / tl, 0.0, 1.0))
+            r2 = (yy - (y0 + t)) ** 2 + (xx - (x0 + 2 * t)) ** 2
+            f = f + depth * g * np.exp(-r2 / (2 * (4.0 + 5.0 * g) ** 2)) + off * np.exp(-r2 / (2 * 12.0 ** 2))
+        wvd[t] = f
+    return wvd.astype(np.float32)
+
+
+def make_growth_multi(meta):
+    import pandas as pd
+    from scipy import ndimage as ndi
+    from tobac_flow.flow import create_flow, Flow
+    from tobac_flow import detection
+    from tobac_flow.label import flow_label
+    from tobac_flow.utils.label_utils import flat_label
+
+    wvd = growth_multi_case()
+    t = pd.date_range("2020-01-01", periods=wvd.shape[0], freq="5min")
+    fg = create_flow(wvd)
+    fq = np.round(fg.forward_flow * 256).astype(np.int16)
+    bq = np.round(fg.backward_flow * 256).astype(np.int16)
+    fg = Flow(fq.astype(np.float32) / 256, bq.astype(np.float32) / 256)
+    da = refshim.DataArray(wvd, coords={"t": t}, dims=("t", "y", "x"), t=t)
+    smoothed, markers = detection.detect_growth_markers(fg, da)
+    markers = np.asarray(markers.data if hasattr(markers, "data") else markers)
+    s2 = ndi.generate_binary_structure(2, 1)[np.newaxis, ...]
+    curv = detection.get_curvature_filter(wvd)
+    opened = ndi.grey_opening(smoothed, footprint=s2)
+    filtered = opened * curv
+    seeds = ndi.binary_opening(filtered >= 0.25, structure=s2)
+    flat = flat_label(seeds != 0)
+    linked = fg.label(seeds)
+    linked_ov = flow_label(fg, seeds, overlap=0.5, absolute_overlap=4)
+    by_len = detection.filter_labels_by_length(linked, 3)
+    gauss = ndi.gaussian_filter(wvd, (0, 2, 2))
+    np.savez_compressed(os.path.join(HERE, "growth_multi.npz"), meta=str(meta), fwd_q256=fq, bwd_q256=bq,
+                        smoothed_even=smoothed[::2].astype(np.float32), gauss_3=gauss[3], opened_5=opened[5],
+                        curv=np.packbits(curv), mask025=np.packbits(filtered >= 0.25), mask05=np.packbits(filtered >= 0.5),
+                        seeds=np.packbits(seeds), flat=flat.astype(np.int16), linked=linked.astype(np.int16),
+                        linked_ov=linked_ov.astype(np.int16), by_len=by_len.astype(np.int16),
+                        markers=markers.astype(np.int16))
+    print("growth_multi: flat", int(flat.max()), "linked", int(linked.max()), "linked_ov", int(linked_ov.max()),
+          "by_len", int(by_len.max()), "markers", int(markers.max()), "px", int((markers > 0).sum()))
+
+
 def main():
     import cv2
     import scipy
@@ -69,6 +130,9 @@ def main():
     from scipy import ndimage as ndi
 
     meta = dict(cv2=cv2.__version__, numpy=np.__version__, scipy=scipy.__version__)
+    if "--only-growth-multi" in sys.argv:
+        make_growth_multi(meta)
+        return
 
     # ---- G1: the survey's known-answer case -------------------------------------------------
     data = synthetic.blob_stack()
@@ -155,6 +219,7 @@ def main():
                         smoothed_even=smoothed[::2].astype(np.float32),
                         mask025=np.packbits(filtered >= 0.25), mask05=np.packbits(filtered >= 0.5), markers=markers.astype(np.int32),
                         n_markers=np.array(int(markers.max())))
+    make_growth_multi(meta)
     print("growth markers:", int(markers.max()), "marked px:", int((markers > 0).sum()))
     for n in ("blob100", "bt_small", "bt_small_production", "three_level", "growth"):
         print(n, os.path.getsize(os.path.join(HERE, n + ".npz")) // 1024, "KiB")

@@ -23,10 +23,13 @@ EXPORTS = (
     "tf_farneback_workspace_bytes", "tf_pair_normalise_u8", "tf_farneback_pairs", "tf_smooth_flow_step",
     "tf_flow_finalise", "tf_sl_convolve", "tf_profile_enable", "tf_profile_reset", "tf_profile_read",
     "tf_vr_default_params", "tf_vr_workspace_bytes", "tf_variational_refinement",
+    "tf_ccl_workspace_bytes", "tf_flat_label", "tf_binary_fill_holes", "tf_gaussian_filter_yx", "tf_curvature_mask",
+    "tf_binary_opening_cross", "tf_grey_opening_cross", "tf_scale_frames", "tf_mask_multiply", "tf_threshold_ge",
+    "tf_label_max", "tf_label_overlap_count", "tf_label_link_groups", "tf_relabel", "tf_label_stats",
 )
 
 KERNEL_CLASSES = ("normalise", "pyramid", "polyexp", "flow_upsample", "fb_iter_coarse", "fb_iter_fullres",
-                  "sl_gather", "smooth_flow", "finalise", "variational_refinement")
+                  "sl_gather", "smooth_flow", "finalise", "variational_refinement", "labelling", "detection_filters")
 
 
 class FbParams(ctypes.Structure):
@@ -85,6 +88,28 @@ def load():
     lib.tf_variational_refinement.argtypes = [vp, vp, vp, ll, vp, ll, ci, ci, ci, ctypes.POINTER(VrParams), vp,
                                               ctypes.c_size_t, vp]
     lib.tf_variational_refinement.restype = ci
+    sz = ctypes.c_size_t
+    lib.tf_ccl_workspace_bytes.argtypes = [ci, ci, ci]
+    lib.tf_ccl_workspace_bytes.restype = sz
+    lib.tf_flat_label.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, sz, vp]
+    lib.tf_binary_fill_holes.argtypes = [vp, vp, ci, ci, ci, vp, sz, vp]
+    lib.tf_gaussian_filter_yx.argtypes = [vp, vp, vp, ci, ci, ci, ci, ctypes.POINTER(cd), ci, vp]
+    lib.tf_curvature_mask.argtypes = [vp, vp, ci, ci, ci, ci, cd, ci, vp]
+    lib.tf_binary_opening_cross.argtypes = [vp, vp, ci, ci, ci, vp]
+    lib.tf_grey_opening_cross.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.tf_scale_frames.argtypes = [vp, vp, vp, ci, ci, ci, vp]
+    lib.tf_mask_multiply.argtypes = [vp, vp, vp, ci, ll, vp]
+    lib.tf_threshold_ge.argtypes = [vp, cd, vp, ci, ll, vp]
+    lib.tf_label_max.argtypes = [vp, ll, vp, vp]
+    lib.tf_label_overlap_count.argtypes = [vp, vp, vp, ll, vp, ci, vp, vp, ll, vp, vp]
+    lib.tf_label_link_groups.argtypes = [vp, vp, ll, vp, ci, cd, ci, vp]
+    lib.tf_relabel.argtypes = [vp, vp, vp, ll, ci, vp]
+    lib.tf_label_stats.argtypes = [vp, vp, vp, ci, ll, ci, vp, vp, vp, vp, vp]
+    lib.tf_label_stats.restype = ci
+    for name in ("tf_flat_label", "tf_binary_fill_holes", "tf_gaussian_filter_yx", "tf_curvature_mask",
+                 "tf_binary_opening_cross", "tf_grey_opening_cross", "tf_scale_frames", "tf_mask_multiply",
+                 "tf_threshold_ge", "tf_label_max", "tf_label_overlap_count", "tf_label_link_groups", "tf_relabel"):
+        getattr(lib, name).restype = ci
     lib.tf_profile_enable.argtypes = [ci]
     lib.tf_profile_read.argtypes = [ci, ctypes.POINTER(cd), ctypes.POINTER(cd), ctypes.POINTER(ll)]
     for name in ("tf_profile_enable", "tf_profile_reset", "tf_profile_read", "tf_fb_level_plan", "tf_fb_poly_constants", "tf_pair_normalise_u8", "tf_farneback_pairs",

@@ -198,9 +198,11 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
     // zero the suffix-sum ring column and the pads of the vertical-sum rows
 #pragma unroll
     for (int s = 0; s < 3 * 3 * 5; ++s) ring[s * NT + tid] = 0.f;
-    for (int i = tid; i < C::VBUF_ROWS * 5 * 2 * C::VPAD; i += NT) {
-        const int rowk = i / (2 * C::VPAD), j = i % (2 * C::VPAD);
-        vbuf[rowk * C::VP + (j < C::VPAD ? j : NT + j)] = 0.f;
+    if constexpr (C::VPAD > 0) {
+        for (int i = tid; i < C::VBUF_ROWS * 5 * 2 * C::VPAD; i += NT) {
+            const int rowk = i / (2 * C::VPAD), j = i % (2 * C::VPAD);
+            vbuf[rowk * C::VP + (j < C::VPAD ? j : NT + j)] = 0.f;
+        }
     }
     // the 13-row window of row r0+j is: rows j..3 of batch b-3 (its full sum minus its prefix P_{j-1}, kept in the
     // ring) + batches b-2, b-1 + prefix P_j of batch b.  Every partial sum is formed fresh from at most 4 values, so

@@ -39,7 +39,7 @@ LevelPlan make_level_plan(int H, int W, const tf_fb_params& p);
 // kernel classes for launch accounting (tf_profile_*)
 enum KClass {
     KC_NORMALISE = 0, KC_PYRAMID, KC_POLYEXP, KC_UPSAMPLE, KC_FB_ITER, KC_FB_ITER_L0, KC_GATHER, KC_SMOOTH, KC_FINALISE,
-    KC_VR, KC_COUNT
+    KC_VR, KC_LABEL, KC_MORPH, KC_COUNT
 };
 
 // RAII launch record: counts launches / algorithmic bytes, and times the enclosed launches with CUDA events on `s`
