@@ -1,0 +1,181 @@
+"""B200-native mirror of the growth-marker detection (``tobac_flow/detection.py:34-125``).
+
+``filtered_tdiff``, ``get_curvature_filter`` and ``detect_growth_markers`` keep the reference's names, arguments and
+results; every array stays in HBM between the Flow operators (diff -> /dt -> 3-frame nanmean -> grey opening x
+curvature filter -> thresholds -> binary opening -> Flow.label -> label filters).  The scipy.ndimage filters the
+reference calls are re-implemented bit-exactly in ``csrc/morph.cu`` / ``csrc/ccl.cu``.  There is no CPU fallback.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from . import analysis
+from . import label as _label
+from .flow import Flow, _as_numpy, _device, _stream, _to_device, _to_host
+
+_T_STRUCT = np.zeros([3, 3, 3])
+_T_STRUCT[:, 1, 1] = 1
+
+
+def _nanmean0(x):
+    return np.nanmean(x, 0)
+
+
+_nanmean0._tf_reducer = _lib.TF_RED_NANMEAN
+
+
+def filtered_tdiff(flow, raw_diff):
+    """detection.py:34-60: 3-frame semi-Lagrangian moving average (nanmean) of a time derivative."""
+    return flow.convolve(raw_diff, structure=_T_STRUCT, func=_nanmean0)
+
+
+def gaussian_kernel1d(sigma: float, truncate: float = 4.0):
+    """The weights scipy.ndimage.gaussian_filter1d builds for order 0 (``_gaussian_kernel1d``) and their radius."""
+    sd = float(sigma)
+    radius = int(truncate * sd + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sd * sd) * x ** 2)
+    return phi / phi.sum(), radius
+
+
+def _float_code(t: torch.Tensor):
+    if t.dtype == torch.float32:
+        return _lib.TF_F32
+    if t.dtype == torch.float64:
+        return _lib.TF_F64
+    raise NotImplementedError(f"dtype {t.dtype} is not supported (float32 / float64 are)")
+
+
+def gaussian_filter_yx_device(field: torch.Tensor, sigma: float) -> torch.Tensor:
+    """ndi.gaussian_filter(field, (0, sigma, sigma)) on a (T, H, W) CUDA tensor."""
+    if sigma <= 1e-15:
+        return field.clone()
+    w, radius = gaussian_kernel1d(sigma)
+    w = np.ascontiguousarray(w[::-1], dtype=np.float64)
+    T, H, W = field.shape
+    tmp, out = torch.empty_like(field), torch.empty_like(field)
+    _lib.check(_lib.load().tf_gaussian_filter_yx(field.data_ptr(), tmp.data_ptr(), out.data_ptr(), _float_code(field),
+                                                 T, H, W, w.ctypes.data_as(_lib.ctypes.POINTER(_lib.ctypes.c_double)),
+                                                 radius, _stream()), "tf_gaussian_filter_yx")
+    return out
+
+
+def curvature_filter_device(field: torch.Tensor, sigma=2, threshold=0, direction="negative") -> torch.Tensor:
+    """``get_curvature_filter`` on a float CUDA tensor -> uint8 mask (T, H, W)."""
+    if direction not in ("negative", "positive"):
+        raise ValueError("Direction must be either positive or negative")
+    lib = _lib.load()
+    T, H, W = field.shape
+    smoothed = gaussian_filter_yx_device(field, sigma)
+    m = torch.empty((T, H, W), dtype=torch.uint8, device=field.device)
+    _lib.check(lib.tf_curvature_mask(smoothed.data_ptr(), m.data_ptr(), _float_code(smoothed), T, H, W, float(threshold),
+                                     int(direction == "positive"), _stream()), "tf_curvature_mask")
+    del smoothed
+    filled = torch.empty_like(m)
+    done = 0
+    while done < T:
+        tc = min(T - done, 65535)
+        ws_bytes = int(lib.tf_ccl_workspace_bytes(tc, H, W))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=field.device)
+        _lib.check(lib.tf_binary_fill_holes(m[done:].data_ptr(), filled[done:].data_ptr(), tc, H, W, ws.data_ptr(),
+                                            ws_bytes, _stream()), "tf_binary_fill_holes")
+        done += tc
+    _lib.check(lib.tf_binary_opening_cross(filled.data_ptr(), m.data_ptr(), T, H, W, _stream()),
+               "tf_binary_opening_cross")
+    return m
+
+
+def get_curvature_filter(field, sigma=2, threshold=0, direction="negative"):
+    """detection.py:64-94: Gaussian-smoothed second differences both beyond the threshold, holes filled, opened."""
+    if direction not in ("negative", "positive"):
+        raise ValueError("Direction must be either positive or negative")
+    t, host = _to_device(field)
+    if not t.dtype.is_floating_point:
+        raise NotImplementedError("get_curvature_filter: integer fields are not supported")
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float32)
+    m = curvature_filter_device(t, sigma, threshold, direction)
+    return _to_host(m).view(np.bool_) if host else m.to(torch.bool)
+
+
+def grey_opening_cross_device(field: torch.Tensor) -> torch.Tensor:
+    T, H, W = field.shape
+    tmp, out = torch.empty_like(field), torch.empty_like(field)
+    _lib.check(_lib.load().tf_grey_opening_cross(field.data_ptr(), tmp.data_ptr(), out.data_ptr(), _float_code(field),
+                                                 T, H, W, _stream()), "tf_grey_opening_cross")
+    return out
+
+
+def time_diff_minutes(t_coord) -> np.ndarray:
+    """``get_time_diff_from_coord`` (tobac_flow/utils/datetime_utils.py:126-166): centred differences in minutes."""
+    import pandas as pd
+    dts = pd.to_datetime(np.asarray(t_coord)).to_pydatetime().tolist()
+    return np.array([(dts[1] - dts[0]).total_seconds() / 60]
+                    + [(dts[i + 2] - dts[i]).total_seconds() / 120 for i in range(len(dts) - 2)]
+                    + [(dts[-1] - dts[-2]).total_seconds() / 60])
+
+
+def growth_markers_device(flow: Flow, wvd: torch.Tensor, dt_minutes) -> dict:
+    """The whole of detection.py:98-118 on device tensors; returns the intermediates the reference exposes plus the
+    markers.  ``wvd`` (T, H, W) float32 CUDA tensor, ``dt_minutes`` T doubles."""
+    lib = _lib.load()
+    dev = wvd.device
+    T, H, W = wvd.shape
+    n = wvd.numel()
+    st = _stream
+    raw32 = flow.diff(wvd)                                                              # detection.py:99
+    dt = torch.from_numpy(np.ascontiguousarray(np.asarray(dt_minutes, np.float64))).to(dev)
+    assert dt.numel() == T
+    raw = torch.empty((T, H, W), dtype=torch.float64, device=dev)
+    _lib.check(lib.tf_scale_frames(raw32.data_ptr(), dt.data_ptr(), raw.data_ptr(), T, H, W, st()), "tf_scale_frames")
+    del raw32
+    smoothed = filtered_tdiff(flow, raw)                                                # :103, float32
+    opened = grey_opening_cross_device(smoothed)                                        # :105-107
+    curv = curvature_filter_device(wvd)                                                 # :108
+    filtered = torch.empty_like(opened)
+    _lib.check(lib.tf_mask_multiply(opened.data_ptr(), curv.data_ptr(), filtered.data_ptr(), _float_code(opened), n,
+                                    st()), "tf_mask_multiply")
+    del opened, curv
+    m025 = torch.empty((T, H, W), dtype=torch.uint8, device=dev)
+    m05 = torch.empty_like(m025)
+    warm = torch.empty_like(m025)
+    _lib.check(lib.tf_threshold_ge(filtered.data_ptr(), 0.25, m025.data_ptr(), _float_code(filtered), n, st()),
+               "tf_threshold_ge")
+    _lib.check(lib.tf_threshold_ge(filtered.data_ptr(), 0.5, m05.data_ptr(), _float_code(filtered), n, st()),
+               "tf_threshold_ge")
+    _lib.check(lib.tf_threshold_ge(wvd.data_ptr(), -5.0, warm.data_ptr(), _float_code(wvd), n, st()), "tf_threshold_ge")
+    seeds = torch.empty_like(m025)
+    _lib.check(lib.tf_binary_opening_cross(m025.data_ptr(), seeds.data_ptr(), T, H, W, st()), "tf_binary_opening_cross")
+    flat, n_flat = _label.flat_label_device(seeds, 1)                                   # Flow.label -> label.py:125
+    linked, _ = _label.link_overlap_device(flow, flat, _label._default_structure(), 0, 1, n_flat)
+    # :114-119: length >= 3, then touches (filtered >= 0.5), then touches (wvd >= -5); three renumberings in the
+    # reference, composed here into one (dropping labels commutes with the order-preserving renumbering)
+    n_labels, tmin, tmax, any_a, any_b = analysis.label_stats_device(linked, m05, warm)
+    wh = ((tmax[1:] - tmin[1:] + 1) >= 3) & (any_a[1:] != 0) & (any_b[1:] != 0)
+    markers = analysis._apply_keep(linked, n_labels, wh)
+    return dict(raw=raw, smoothed=smoothed, filtered=filtered, seeds=seeds, flat=flat, linked=linked, markers=markers)
+
+
+def detect_growth_markers(flow, wvd):
+    """detection.py:98-125: returns (wvd_diff_smoothed, marker_labels).
+
+    ``wvd`` is an ``xr.DataArray``-like with a ``.t`` time coordinate (results are numpy, wrapped back into the
+    input's type when it offers ``coords`` / ``dims``), or a CUDA tensor with a ``t`` attribute (results stay on the
+    device).
+    """
+    t_coord = getattr(wvd, "t", None)
+    if t_coord is None:
+        raise AttributeError("wvd needs a time coordinate `.t` (detection.py:100)")
+    dt = time_diff_minutes(t_coord)
+    on_device = isinstance(wvd, torch.Tensor) and wvd.is_cuda
+    w, _ = _to_device(wvd if isinstance(wvd, torch.Tensor) else _as_numpy(wvd), torch.float32)
+    r = growth_markers_device(flow, w, dt)
+    if on_device:
+        return r["smoothed"], r["markers"]
+    smoothed, markers = _to_host(r["smoothed"]), _to_host(r["markers"])
+    if hasattr(wvd, "coords") and hasattr(wvd, "dims") and not isinstance(wvd, np.ndarray):
+        try:
+            markers = type(wvd)(markers, wvd.coords, wvd.dims)                          # detection.py:121-123
+        except Exception:
+            pass
+    return smoothed, markers

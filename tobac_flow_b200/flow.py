@@ -424,7 +424,8 @@ class Flow:
         return self.convolve(data, structure=np.ones((3, 3, 3), bool), method=method, fill_value=fill_value,
                              dtype=dtype, func=sobel_reducer(direction))
 
-    # -- downstream consumers (out of the hot-path scope; they stay the reference's own numpy code) -----------------
+    # -- downstream consumers ---------------------------------------------------------------------------------------
+    # watershed (and label with sub-segmentation) stay the reference's own code; label / link_overlap are native
     def _delegate(self, name, *args, **kwargs):
         try:
             import tobac_flow.flow as ref  # the reference package, when installed next to this one
@@ -439,18 +440,25 @@ class Flow:
 
     def label(self, data, structure=None, dtype: type = np.int32, overlap: float = 0, absolute_overlap: int = 1,
               subsegment_shrink: float = 0, peak_min_distance: int = 5):
+        """``Flow.label`` (tobac_flow/flow.py:281-330 -> tobac_flow/label.py:84-175)."""
         if structure is None:
             structure = _default_structure()
-        return self._delegate("label", data, structure=structure, dtype=dtype, overlap=overlap,
-                              absolute_overlap=absolute_overlap, subsegment_shrink=subsegment_shrink,
-                              peak_min_distance=peak_min_distance)
+        if subsegment_shrink != 0:   # skimage sub-segmentation: not on the path, the reference's own code handles it
+            return self._delegate("label", data, structure=structure, dtype=dtype, overlap=overlap,
+                                  absolute_overlap=absolute_overlap, subsegment_shrink=subsegment_shrink,
+                                  peak_min_distance=peak_min_distance)
+        from .label import flow_label
+        return flow_label(self, data, structure=structure, dtype=dtype, overlap=overlap,
+                          absolute_overlap=absolute_overlap)
 
     def link_overlap(self, data, structure=None, dtype: type = np.int32, overlap: float = 0,
                      absolute_overlap: int = 1):
+        """``Flow.link_overlap`` (tobac_flow/flow.py:332-355 -> tobac_flow/label.py:249-321)."""
         if structure is None:
             structure = _default_structure()
-        return self._delegate("link_overlap", data, structure=structure, dtype=dtype, overlap=overlap,
-                              absolute_overlap=absolute_overlap)
+        from .label import flow_link_overlap
+        return flow_link_overlap(self, data, structure=structure, dtype=dtype, overlap=overlap,
+                                 absolute_overlap=absolute_overlap)
 
 
 _DIFF = _tag(_lib.TF_RED_DIFF)(diff_func)
