@@ -17,6 +17,10 @@
 //     stores the new flow (32 B per thread, coalesced).
 //   * forward and backward CTAs of the same pair and strip are adjacent in launch order, so the second reader of the
 //     shared R planes hits L2.
+//   * work distribution (default, TF_PERSIST=0 restores the chunk grid): all (pair, strip) columns are laid end to end
+//     and one resident wave of forward/backward CTA pairs takes equal spans of that row space (measured +2 %).
+// Measured and rejected: inheriting a row's top taps from the previous row's bottom taps (per-lane predicated loads,
+// 168 registers, 3 CTAs/SM): 113 ms vs 94.5 ms per 96-frame step for the full-resolution level.
 // Algorithmic HBM bytes per pixel-iteration: flow 8 + R0 20 + R1 20 read, flow 8 written = 56 B.
 #include <stdlib.h>
 
@@ -164,15 +168,38 @@ template <int NT, int HK, bool HS>
 __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : (HS ? TF_HS_CTAS : 4)))
 fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const float* __restrict__ flow_in,
                      float* __restrict__ out_fwd, long long fwd_stride, float* __restrict__ out_bwd,
-                     long long bwd_stride, int h, int w, int chunk_rows, float clampv) {
+                     long long bwd_stride, int h, int w, int chunk_rows, float clampv, int strips, int span, int total) {
     using C = StripCfg<NT, HK, HS>;
     extern __shared__ __align__(16) float smem[];
     float* ring = smem;                       // [batch % 3][P0..P2][k][col]: prefix sums of the batch's rows
     float* vbuf = smem + C::RING_FLOATS;      // [buf][row][k][VP]
     const int tid = threadIdx.x;
-    const int strip = blockIdx.x >> 1, dir = blockIdx.x & 1;
-    const int pair = blockIdx.z;
+    const int dir = blockIdx.x & 1;
     const int plane = h * w;
+    // Work distribution.  span == 0: one (strip, chunk, pair) per CTA from the grid.  span > 0 (persistent): the
+    // (pair, strip) columns are laid end to end into one row space of `total` = n_pairs * strips * h rows and CTA pair
+    // s (forward + backward) marches rows [s * span, (s + 1) * span) of it, restarting the window at every column
+    // boundary it crosses: one wave of equally loaded CTAs, warm-up rows paid once or twice per CTA instead of per chunk.
+    // (the span bounds are recomputed from %ctaid at every column instead of being kept live across the row loop)
+    auto cta_pair = []() { unsigned v; asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(v)); return (int)(v >> 1); };
+    int col = span > 0 ? (cta_pair() * span) / h : 0;
+    for (bool first = true;; first = false, ++col) {
+    int strip, pair, yc0, yc1;
+    if (span > 0) {
+        const int lin0 = cta_pair() * span, lin1 = min(lin0 + span, total);
+        if (col * h >= lin1) break;
+        pair = col / strips;
+        strip = col - pair * strips;
+        yc0 = max(lin0 - col * h, 0);
+        yc1 = min(lin1 - col * h, h);
+        if (!first) __syncthreads();          // the previous segment's last H phase is done with the shared buffers
+    } else {
+        if (!first) break;
+        strip = blockIdx.x >> 1;
+        pair = blockIdx.z;
+        yc0 = blockIdx.y * chunk_rows;
+        yc1 = min(yc0 + chunk_rows, h);
+    }
     const float* Rp = R + (long long)(2 * pair) * img_stride;
     const float* Rn = Rp + img_stride;
     const float* R0 = dir ? Rn : Rp;
@@ -186,8 +213,6 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
     float2* fout = reinterpret_cast<float2*>(dir ? out_bwd + (long long)pair * bwd_stride
                                                  : out_fwd + (long long)pair * fwd_stride);
     const int x0 = strip * C::OUT_W;
-    const int yc0 = blockIdx.y * chunk_rows;
-    const int yc1 = min(yc0 + chunk_rows, h);
 
     // M-phase identity: one column of the strip (replicate-clamped = the box filter's border rule)
     const int gx = min(max(x0 - IT_HALO + tid, 0), w - 1);
@@ -339,6 +364,7 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
             const int c0 = HK * cg;                        // region column of o[0]
             const int xg = x0 - IT_HALO + c0;              // image column of o[0]
             float2* dst = fout + (long long)y * w + xg;
+            // (pairing the outputs into 16-byte stores on even widths measured 2 % slower than four 8-byte stores)
 #pragma unroll
             for (int i = 0; i < HK; ++i) {
                 const int c = c0 + i;
@@ -347,6 +373,7 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
         }
         if (HK == 8) __syncthreads();   // single vertical-sum buffer: the next M batch overwrites it
     }
+    }   // segments
 }
 
 template <int NT, int HK, bool HS = false>
@@ -359,8 +386,20 @@ static void launch_strip(const float* R, long long img_stride, const float* flow
         attr_set = true;
     }
     const int strips = cdiv(w, C::OUT_W);
-    // rows per chunk: minimise (waves of resident CTAs) x (rows a CTA marches, incl. its 12 warm-up rows)
     const long long slots = 148LL * (NT == 256 ? 2 : (HS ? TF_HS_CTAS : 4));
+    static const char* env_persist = getenv("TF_PERSIST");
+    const bool persist = env_persist ? atoi(env_persist) != 0 : true;
+    const long long total = (long long)n_pairs * strips * h;
+    if (persist && total < 0x40000000LL) {
+        // one resident wave: `slots / 2` forward/backward CTA pairs share the linearised rows equally; at tiny levels a
+        // CTA still gets at least 24 rows so the warm-up rows do not dominate
+        const int span = (int)max((total + slots / 2 - 1) / (slots / 2), 24LL);
+        const int n_cta_pairs = (int)((total + span - 1) / span);
+        fb_iter_strip_kernel<NT, HK, HS><<<2 * n_cta_pairs, NT, C::SMEM_BYTES, s>>>(
+            R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, h, w, 0, clamp, strips, span, (int)total);
+        return;
+    }
+    // rows per chunk: minimise (waves of resident CTAs) x (rows a CTA marches, incl. its 12 warm-up rows)
     int chunks = 1;
     long long best = -1;
     for (int c = 1; c <= max(1, h / 16); ++c) {
@@ -376,7 +415,8 @@ static void launch_strip(const float* R, long long img_stride, const float* flow
         fb_iter_strip_kernel<NT, HK, HS><<<g, NT, C::SMEM_BYTES, s>>>(R + (long long)(2 * p0) * img_stride, img_stride,
                                                               flow_in + (long long)(2 * p0) * 2 * h * w,
                                                               out_fwd + p0 * fwd_stride, fwd_stride,
-                                                              out_bwd + p0 * bwd_stride, bwd_stride, h, w, chunk_rows, clamp);
+                                                              out_bwd + p0 * bwd_stride, bwd_stride, h, w, chunk_rows, clamp,
+                                                              strips, 0, 0);
     }
 }
 
