@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-detection", action="store_true", help="skip the detect_growth_markers extra (not the metric)")
+    ap.add_argument("--detection-frames", type=int, default=48)
     ap.add_argument("--ref-workers", type=int, default=0)
     return ap.parse_args()
 
@@ -401,6 +403,29 @@ def run_b200(args):
                "note": "create_flow + diff + sobel + convolve via the numpy API; input pinned, each operator uploads "
                        "its operand and returns a host array; flows stay on the device (Flow keeps them resident)"}
 
+    # ---- extra (not the metric): the device-resident growth-marker detection on this rank's first frames ---------------
+    detection = None
+    if not args.no_detection and rank == 0:
+        from tobac_flow_b200.detection import growth_markers_device
+        Td = min(args.detection_frames, T)
+        wvd = synthetic.wvd_from_bt(shard.buf[1:1 + Td]).float().contiguous()
+        fl_d = tfb.Flow(fwd[:Td], bwd[:Td])
+        dtm = np.full(Td, 5.0)
+        growth_markers_device(fl_d, wvd, dtm)
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(3):
+            r = growth_markers_device(fl_d, wvd, dtm)
+        d1.record()
+        torch.cuda.synchronize()
+        dms = d0.elapsed_time(d1) / 3
+        detection = {"what": "detect_growth_markers on device tensors (diff, /dt, 3-frame nanmean, grey opening x "
+                             "curvature filter, thresholds, opening, flow_label, label filters), flow given",
+                     "frames": Td, "ms": dms, "frames_per_s": Td / (dms / 1e3),
+                     "flat_labels": int(r["flat"].max()), "linked_labels": int(r["linked"].max())}
+        del wvd, r
+
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -419,7 +444,7 @@ def run_b200(args):
                                    "Farneback per pair + Flow.diff + Flow.sobel(linear, f64) + Flow.convolve(7-tap stack)",
                        "frames_per_gpu": T, "height": H, "width": W, "pyramid_levels": L,
                        "l2": "inputs (4.3 GB of frames per GPU) are far larger than the 126 MB L2; no explicit flush"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches // max(args.steps, 1) * args.steps,
+            "clocks": clocks, "e2e": e2e, "detection": detection, "gpu_launches": launches // max(args.steps, 1) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line))

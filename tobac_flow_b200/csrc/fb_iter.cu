@@ -19,7 +19,8 @@
 //     shared R planes hits L2.
 //   * work distribution (default, TF_PERSIST=0 restores the chunk grid): all (pair, strip) columns are laid end to end
 //     and one resident wave of forward/backward CTA pairs takes equal spans of that row space (measured +2 %).
-// Measured and rejected: inheriting a row's top taps from the previous row's bottom taps (per-lane predicated loads,
+// Measured and rejected: two rows of taps in flight per thread (168 registers, 3 CTAs/SM: 126-144 ms vs 94.5 ms; a warp
+// has six scoreboards, already taken by cur / next taps, the flow queue and the shared-memory reads); inheriting a row's top taps from the previous row's bottom taps (per-lane predicated loads,
 // 168 registers, 3 CTAs/SM): 113 ms vs 94.5 ms per 96-frame step for the full-resolution level.
 // Algorithmic HBM bytes per pixel-iteration: flow 8 + R0 20 + R1 20 read, flow 8 written = 56 B.
 #include <stdlib.h>
@@ -33,6 +34,10 @@ constexpr int IT_HALO = 6, IT_WIN = 13, IT_RB = 4;
 #define TF_L2_PREFETCH_ROWS 0
 #endif
 constexpr int IT_PREFETCH_ROWS = TF_L2_PREFETCH_ROWS;
+#define TF_PF 1      // rows of taps in flight ahead of the row being computed
+#ifndef TF_FQ
+#define TF_FQ 4      // rows the flow loads run ahead of the tap issue that consumes them (4 or 2)
+#endif
 #ifndef TF_HS_CTAS
 #define TF_HS_CTAS 4
 #endif   // measured: no gain on B200, so off
@@ -246,9 +251,9 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
     auto row_y = [&](int i) { return min(max(r_begin + i, 0), h - 1); };
     Taps cur;
     issue_taps(cur, RP, w, h, gx, row_y(0), ld_stream(fin + row_y(0) * w + gx));
-    float2 fq[IT_RB];            // flows of rows i+1 .. i+4 (a DRAM round trip ahead of their use)
+    float2 fq[TF_FQ];            // flows of rows i+PF .. i+PF+FQ-1 (a DRAM round trip ahead of their use)
 #pragma unroll
-    for (int j = 0; j < IT_RB; ++j) fq[j] = ld_stream(fin + row_y(1 + j) * w + gx);
+    for (int j = 0; j < TF_FQ; ++j) fq[j] = ld_stream(fin + row_y(TF_PF + j) * w + gx);
     __syncthreads();
 
     for (int b = 0; b < n_batches; ++b) {
@@ -263,8 +268,8 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
             const int i = b * IT_RB + j;
             // prefetch: the next row's taps (its flow was requested four rows ago) and the flow of row i+5
             Taps nxt;
-            issue_taps(nxt, RP, w, h, gx, row_y(i + 1), fq[j]);
-            fq[j] = ld_stream(fin + row_y(i + 1 + IT_RB) * w + gx);
+            issue_taps(nxt, RP, w, h, gx, row_y(i + TF_PF), fq[j % TF_FQ]);
+            fq[j % TF_FQ] = ld_stream(fin + row_y(i + TF_PF + TF_FQ) * w + gx);
             if (IT_PREFETCH_ROWS > 0) {
                 // pull the R rows this column will gather from a few rows later into L2 (both images: R0 and R1)
                 const int op = row_y(i + IT_PREFETCH_ROWS) * w + gx;
