@@ -19,8 +19,9 @@
 //     shared R planes hits L2.
 //   * work distribution (default, TF_PERSIST=0 restores the chunk grid): all (pair, strip) columns are laid end to end
 //     and one resident wave of forward/backward CTA pairs takes equal spans of that row space (measured +2 %).
-// Measured and rejected: cp.async.bulk.prefetch.L2 of the strip's next rows (five bulk prefetches per row from warp 0,
-// 4-16 rows ahead: 130-134 ms vs 95 ms); two rows of taps in flight per thread (168 registers, 3 CTAs/SM: 126-144 ms vs 94.5 ms; a warp
+// Measured and rejected: pulling the strip's next rows into L2 ahead of the march, either with five
+// cp.async.bulk.prefetch.L2 per row or with one prefetch.global.L2 per 128-byte line from warp 0, 4-16 rows ahead
+// (117-134 ms vs 95 ms: the extra work of one warp delays the whole CTA at the batch barrier); two rows of taps in flight per thread (168 registers, 3 CTAs/SM: 126-144 ms vs 94.5 ms; a warp
 // has six scoreboards, already taken by cur / next taps, the flow queue and the shared-memory reads); inheriting a row's top taps from the previous row's bottom taps (per-lane predicated loads,
 // 168 registers, 3 CTAs/SM): 113 ms vs 94.5 ms per 96-frame step for the full-resolution level.
 // Algorithmic HBM bytes per pixel-iteration: flow 8 + R0 20 + R1 20 read, flow 8 written = 56 B.

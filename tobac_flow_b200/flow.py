@@ -13,6 +13,7 @@ Differences by design (device residency):
   chained operators (``diff`` -> ``filtered_tdiff``) stay on the device.
 """
 import ctypes
+import os
 from functools import partial
 from typing import Callable
 
@@ -490,7 +491,7 @@ def _pair_batch(n_pairs: int, H: int, W: int, params, vr: bool = False) -> int:
         per_pair += int(_lib.load().tf_vr_workspace_bytes(1, H, W))
     free, _ = torch.cuda.mem_get_info()
     by_mem = max(1, int(free * 0.6) // per_pair)
-    by_px = max(1, (96 << 20) // (H * W))
+    by_px = max(1, (int(os.environ.get("TF_PAIR_BATCH_MPX", "256")) << 20) // (H * W))
     return max(1, min(n_pairs, by_mem, by_px))
 
 
