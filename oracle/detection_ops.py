@@ -19,6 +19,9 @@ Reference lines followed:
   filtered_tdiff            tobac_flow/detection.py:34-60
   get_curvature_filter      tobac_flow/detection.py:64-94
   detect_growth_markers     tobac_flow/detection.py:98-125
+  get_growth_rate           tobac_flow/detection.py:168-198
+  get_anvil_markers         tobac_flow/detection.py:494-516 (find_object_lengths analysis.py:15-35,
+                            remap_labels utils/label_utils.py:265-307)
 """
 import numpy as np
 from scipy import ndimage as ndi
@@ -169,3 +172,36 @@ def detect_growth_markers(wvd, dt_minutes, fwd, bwd, backend="numpy", intermedia
     if intermediates:
         return dict(raw=raw, smoothed=smoothed, filtered=filtered, seeds=seeds, linked=linked, markers=markers)
     return smoothed, markers
+
+
+def get_growth_rate(field, dt_minutes, fwd, bwd, method="linear", backend="numpy"):
+    """detection.py:168-198: time derivative, then the nanmean over the 5-point same-step cross."""
+    field = np.asarray(field)
+    growth = ops.diff(field, fwd, bwd, method=method, backend=backend) / np.asarray(dt_minutes, np.float64)[:, np.newaxis, np.newaxis]
+    s_struct = cross3()
+    s_struct[0] = 0
+    s_struct[2] = 0
+    return ops.convolve(growth, fwd, bwd, structure=s_struct, method=method, func=ops.nanmean_reducer, backend=backend)
+
+
+def find_object_lengths(labels):
+    """analysis.py:15-35."""
+    return np.array([o[0].stop - o[0].start for o in ndi.find_objects(labels)])
+
+
+def remap_labels(labels, locations):
+    """utils/label_utils.py:265-307 for a boolean `locations` (the only form the detection path uses)."""
+    remapper = np.zeros(np.nanmax(labels) + 1, labels.dtype)
+    remapper[1:][locations] = np.arange(1, np.sum(locations) + 1)
+    return remapper[labels]
+
+
+def get_anvil_markers(field, fwd, bwd, threshold=-5, overlap=0.5, absolute_overlap=5, min_length=3, backend="numpy"):
+    """detection.py:494-516 with subsegment_shrink == 0."""
+    structure = cross3()
+    s_struct = structure * np.array([0, 1, 0])[:, np.newaxis, np.newaxis].astype(bool)
+    mask = ndi.binary_opening(np.asarray(field) >= threshold, structure=s_struct)
+    labels = flow_label(mask, fwd, bwd, overlap=overlap, absolute_overlap=absolute_overlap, backend=backend)
+    if labels.max() == 0:
+        return labels
+    return remap_labels(labels, find_object_lengths(labels) > min_length)

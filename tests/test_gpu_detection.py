@@ -241,3 +241,27 @@ def test_detect_growth_markers_with_own_flow_and_nans():
     assert np.array_equal(r["linked"].cpu().numpy(), want["linked"])
     assert np.array_equal(r["markers"].cpu().numpy(), want["markers"])
     assert want["markers"].max() >= 1
+
+
+@pytest.mark.parametrize("method", ["linear", "cubic"])
+def test_get_growth_rate(multi, method):
+    import pandas as pd
+    import refshim
+    from tobac_flow_b200.detection import get_growth_rate
+    g, wvd, fwd, bwd, flow = multi
+    t = pd.date_range("2020-01-01", periods=wvd.shape[0], freq="5min")
+    da = refshim.DataArray(wvd, coords={"t": t}, dims=("t", "y", "x"), t=t)
+    got = get_growth_rate(flow, da, method=method)
+    want = det.get_growth_rate(wvd, np.full(wvd.shape[0], 5.0), fwd, bwd, method=method, backend=BACKEND)
+    assert got.dtype == np.float32 and np.array_equal(got, want, equal_nan=True)
+
+
+def test_get_anvil_markers(multi):
+    from tobac_flow_b200.detection import get_anvil_markers
+    g, wvd, fwd, bwd, flow = multi
+    for thr, ov, ab, ml in ((-5, 0.5, 5, 3), (-12, 0.2, 1, 1), (5, 0.5, 5, 3)):
+        want = det.get_anvil_markers(wvd, fwd, bwd, threshold=thr, overlap=ov, absolute_overlap=ab, min_length=ml,
+                                     backend=BACKEND)
+        got = get_anvil_markers(flow, wvd, threshold=thr, overlap=ov, absolute_overlap=ab, min_length=ml)
+        assert np.array_equal(got, want), (thr, ov, ab, ml)
+    assert det.get_anvil_markers(wvd, fwd, bwd, backend=BACKEND).max() >= 1

@@ -386,3 +386,27 @@ def test_variational_refinement_vs_opencv(tfb, shape):
     rf, rb = ops.create_flow(bt, vr_steps=1, backend="cv2" if ops.have_cv2() else "numpy")
     assert_flow_close(f.forward_flow, rf, 2e-3, 2e-2)
     assert_flow_close(f.backward_flow, rb, 2e-3, 2e-2)
+
+
+def test_sobel_around_nan_inf_and_wild_flow():
+    """Flow.sobel next to NaN pixels, NaN stripes, an all-NaN frame, Inf values, NaN / huge flow vectors and samples far
+    outside the image: identical NaN mask and 1e-12 relative agreement with the oracle."""
+    import tobac_flow_b200 as tfb
+    bt = synthetic.bt_sequence(6, 203, 331, seed=77, nans=True)
+    bt[2, 50:53, 100:140] = np.nan
+    bt[3, 120, 200] = np.inf
+    bt[4] = np.nan
+    rng = np.random.default_rng(5)
+    fwd = (rng.standard_normal(bt.shape + (2,)) * 1.5).astype(np.float32)
+    bwd = (rng.standard_normal(bt.shape + (2,)) * 1.5).astype(np.float32)
+    fwd[1, 10, 10] = np.nan
+    bwd[1, 20, 20] = 1e9
+    fwd[0, :, :5] = 30.0          # samples far outside the image on the left
+    got = tfb.Flow(fwd, bwd).sobel(bt)
+    assert got.dtype == np.float64
+    with np.errstate(all="ignore"):
+        want = ops.sobel(bt, fwd, bwd, dtype=None, backend="cv2" if ops.have_cv2() else "numpy")
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(np.isinf(got), np.isinf(want))
+    ok = np.isfinite(want)
+    assert np.max(np.abs(got[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1.0)) < 1e-12

@@ -129,3 +129,38 @@ def test_link_groups_random_graph():
             want = det.link_flat_labels(flat, back, fwd_l, np.int32, overlap, absolute)
             got, n = _link_groups_c(flat, back, fwd_l, overlap, absolute)
             assert np.array_equal(got, want), (trial, overlap, absolute)
+
+
+def test_growth_rate_and_anvil_markers_against_the_unmodified_reference(multi):
+    """Build container only (skipped where /root/reference is absent): the oracle's get_growth_rate and
+    get_anvil_markers against the reference's own functions run under the dependency stubs."""
+    import refshim
+    if not refshim.reference_available():
+        pytest.skip("reference not available")
+    import sys
+    import pandas as pd
+    saved_path, saved_modules = list(sys.path), set(sys.modules)
+    try:
+        refshim.load_reference()
+        from tobac_flow.flow import Flow
+        from tobac_flow import detection
+        g, wvd, fwd, bwd, r = multi
+        fl = Flow(fwd, bwd)
+        t = pd.date_range("2020-01-01", periods=wvd.shape[0], freq="5min")
+        da = refshim.DataArray(wvd, coords={"t": t}, dims=("t", "y", "x"), t=t)
+        dt = np.full(wvd.shape[0], 5.0)
+        for m in ("linear", "cubic"):
+            assert np.array_equal(detection.get_growth_rate(fl, da, method=m),
+                                  det.get_growth_rate(wvd, dt, fwd, bwd, method=m, backend="cv2"), equal_nan=True)
+        anvil = getattr(detection.get_anvil_markers, "__wrapped__", detection.get_anvil_markers)
+        for kw in (dict(), dict(threshold=-12, overlap=0.2, absolute_overlap=1, min_length=1)):
+            assert np.array_equal(np.asarray(anvil(fl, wvd, **kw)),
+                                  det.get_anvil_markers(wvd, fwd, bwd, backend="cv2", **kw))
+    finally:
+        # the reference's path entry (it has its own `tests` package) and the dependency stubs must not leak into
+        # the rest of the session
+        sys.path[:] = saved_path
+        for name in set(sys.modules) - saved_modules:
+            if name.split(".")[0] in ("tobac_flow", "xarray", "pyproj", "skimage"):
+                del sys.modules[name]
+        refshim._loaded = None

@@ -156,6 +156,68 @@ def growth_markers_device(flow: Flow, wvd: torch.Tensor, dt_minutes) -> dict:
     return dict(raw=raw, smoothed=smoothed, filtered=filtered, seeds=seeds, flat=flat, linked=linked, markers=markers)
 
 
+def _time_coord(field):
+    t_coord = getattr(field, "t", None)
+    if t_coord is None:
+        raise AttributeError("the field needs a time coordinate `.t`")
+    return time_diff_minutes(t_coord)
+
+
+def growth_rate_device(flow: Flow, field: torch.Tensor, dt_minutes, method: str = "linear") -> torch.Tensor:
+    """``get_growth_rate`` on a float32 CUDA tensor: Flow.diff / dt, then the 5-point same-step nanmean (float32)."""
+    T, H, W = field.shape
+    raw32 = flow.diff(field, method=method)
+    dt = torch.from_numpy(np.ascontiguousarray(np.asarray(dt_minutes, np.float64))).to(field.device)
+    assert dt.numel() == T
+    raw = torch.empty((T, H, W), dtype=torch.float64, device=field.device)
+    _lib.check(_lib.load().tf_scale_frames(raw32.data_ptr(), dt.data_ptr(), raw.data_ptr(), T, H, W, _stream()),
+               "tf_scale_frames")
+    del raw32
+    s_struct = np.zeros((3, 3, 3), bool)
+    s_struct[1, 1, :] = s_struct[1, :, 1] = True
+    return flow.convolve(raw, structure=s_struct, func=_nanmean0, method=method)
+
+
+def get_growth_rate(flow, field, method: str = "linear"):
+    """detection.py:168-198: growth / cooling rate of ``field`` (an array with a ``.t`` time coordinate)."""
+    dt = _time_coord(field)
+    on_device = isinstance(field, torch.Tensor) and field.is_cuda
+    f, _ = _to_device(field if isinstance(field, torch.Tensor) else _as_numpy(field), torch.float32)
+    r = growth_rate_device(flow, f, dt, method)
+    return r if on_device else _to_host(r)
+
+
+def anvil_markers_device(flow: Flow, field: torch.Tensor, threshold=-5, overlap=0.5, absolute_overlap=5,
+                         min_length=3) -> torch.Tensor:
+    """``get_anvil_markers`` on a float CUDA tensor (subsegment_shrink == 0)."""
+    lib = _lib.load()
+    T, H, W = field.shape
+    m = torch.empty((T, H, W), dtype=torch.uint8, device=field.device)
+    _lib.check(lib.tf_threshold_ge(field.data_ptr(), float(threshold), m.data_ptr(), _float_code(field), field.numel(),
+                                   _stream()), "tf_threshold_ge")
+    opened = torch.empty_like(m)
+    _lib.check(lib.tf_binary_opening_cross(m.data_ptr(), opened.data_ptr(), T, H, W, _stream()), "tf_binary_opening_cross")
+    del m
+    flat, n_flat = _label.flat_label_device(opened, 1)
+    linked, _ = _label.link_overlap_device(flow, flat, _label._default_structure(), overlap, absolute_overlap, n_flat)
+    n_labels, tmin, tmax, _, _ = analysis.label_stats_device(linked)
+    wh = (tmax[1:] - tmin[1:] + 1) > min_length        # find_object_lengths(...) > min_length, then remap_labels
+    return analysis._apply_keep(linked, n_labels, wh)
+
+
+def get_anvil_markers(flow, field, threshold=-5, overlap=0.5, absolute_overlap=5, subsegment_shrink=0, min_length=3):
+    """detection.py:494-516 (without the DataArray decoration): opened ``field >= threshold`` mask, linked along the
+    flow, labels no longer than ``min_length`` steps dropped and the rest renumbered."""
+    if subsegment_shrink != 0:
+        raise NotImplementedError("subsegment_shrink != 0 (skimage watershed sub-segmentation) is not built here")
+    on_device = isinstance(field, torch.Tensor) and field.is_cuda
+    f, _ = _to_device(field if isinstance(field, torch.Tensor) else _as_numpy(field))
+    if f.dtype not in (torch.float32, torch.float64):
+        f = f.to(torch.float32)
+    r = anvil_markers_device(flow, f, threshold, overlap, absolute_overlap, min_length)
+    return r if on_device else _to_host(r)
+
+
 def detect_growth_markers(flow, wvd):
     """detection.py:98-125: returns (wvd_diff_smoothed, marker_labels).
 
