@@ -397,7 +397,9 @@ static void launch_strip(const float* R, long long img_stride, const float* flow
     static const char* env_persist = getenv("TF_PERSIST");
     const bool persist = env_persist ? atoi(env_persist) != 0 : true;
     const long long total = (long long)n_pairs * strips * h;
-    if (persist && total < 0x40000000LL) {
+    static const char* env_min = getenv("TF_PERSIST_MIN_ROWS");
+    const long long min_rows = env_min ? atoll(env_min) : 128;   // below this the chunk grid's extra parallelism wins
+    if (persist && total < 0x40000000LL && total >= min_rows * (slots / 2)) {
         // one resident wave: `slots / 2` forward/backward CTA pairs share the linearised rows equally; at tiny levels a
         // CTA still gets at least 24 rows so the warm-up rows do not dominate
         const int span = (int)max((total + slots / 2 - 1) / (slots / 2), 24LL);
