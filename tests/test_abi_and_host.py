@@ -107,3 +107,51 @@ def test_synthetic_numpy_and_torch_agree():
     assert np.array_equal(np.isnan(a), np.isnan(b))
     assert np.nanmax(np.abs(a - b)) < 1e-3
     assert np.isnan(a).sum() > 0
+
+
+def test_detection_abi_argument_checks(lib):
+    """The detection / labelling entry points reject bad arguments with a status code before touching CUDA."""
+    L = lib.load()
+    assert L.tf_ccl_workspace_bytes(0, 10, 10) == 0
+    n = L.tf_ccl_workspace_bytes(3, 100, 200)
+    assert n >= 3 * 100 * 200 * 5                                  # int32 parents + one flag byte per pixel
+    assert L.tf_flat_label(None, None, 1, 4, 4, 1, None, None, 0, None) == -1
+    assert L.tf_flat_label(None, None, 0, 4, 4, 1, None, None, 0, None) == 0          # empty stack: nothing to do
+    assert L.tf_binary_fill_holes(None, None, 2, 4, 4, None, 0, None) == -1
+    w = (ctypes.c_double * 3)(0.25, 0.5, 0.25)
+    assert L.tf_gaussian_filter_yx(None, None, None, 0, 1, 4, 4, w, 1, None) == -1
+    assert L.tf_curvature_mask(None, None, 0, 1, 4, 4, 0.0, 0, None) == -1
+    assert L.tf_binary_opening_cross(None, None, 1, 4, 4, None) == -1
+    assert L.tf_grey_opening_cross(None, None, None, 0, 1, 4, 4, None) == -1
+    assert L.tf_scale_frames(None, None, None, 1, 4, 4, None) == -1
+    assert L.tf_mask_multiply(None, None, None, 0, 16, None) == -1
+    assert L.tf_threshold_ge(None, 0.0, None, 0, 16, None) == -1
+    assert L.tf_label_max(None, 16, None, None) == -1
+    assert L.tf_relabel(None, None, None, 16, 3, None) == -1
+    assert L.tf_label_stats(None, None, None, 1, 16, 3, None, None, None, None, None) == -1
+    assert L.tf_label_overlap_count(None, None, None, 16, None, 3, None, None, 64, None, None) == -1
+    assert b"invalid argument" in L.tf_last_error()
+    # the host-side linking walk works without a GPU: two labels linked by one forward edge of 3 pixels
+    keys = np.array([(1 << 31) | 2, 0xFFFFFFFFFFFFFFFF], np.uint64)
+    counts = np.array([3, 0], np.int32)
+    sizes = np.array([0, 5, 4, 2], np.int32)
+    out = np.zeros(4, np.int32)
+    assert L.tf_label_link_groups(keys.ctypes.data, counts.ctypes.data, 2, sizes.ctypes.data, 3, ctypes.c_double(0.5), 1,
+                                  out.ctypes.data) == 2
+    assert out.tolist() == [0, 1, 1, 2]
+    assert L.tf_label_link_groups(keys.ctypes.data, counts.ctypes.data, 2, sizes.ctypes.data, 3, ctypes.c_double(0.8), 1,
+                                  out.ctypes.data) == 3                               # 3 < 0.8 * min(5, 4): not linked
+    assert out.tolist() == [0, 1, 2, 3]
+
+
+def test_detection_host_helpers():
+    """Pure host logic of the detection mirror: scipy's Gaussian weights and the centred time differences."""
+    from scipy.ndimage import _filters
+    from tobac_flow_b200.detection import gaussian_kernel1d, time_diff_minutes
+    import pandas as pd
+    for sigma in (0.5, 1.0, 2.0, 3.3):
+        w, r = gaussian_kernel1d(sigma)
+        assert r == int(4.0 * sigma + 0.5)
+        assert np.array_equal(w, _filters._gaussian_kernel1d(sigma, 0, r))
+    t = pd.to_datetime(["2020-01-01 00:00", "2020-01-01 00:05", "2020-01-01 00:15", "2020-01-01 00:16"])
+    assert np.array_equal(time_diff_minutes(t), [5.0, 7.5, 5.5, 1.0])
