@@ -5,6 +5,8 @@
 // Only the source rows/columns the bilinear resize actually reads are blurred: pass A blurs vertically at the
 // (at most two) source rows of every destination row, pass B blurs those rows horizontally at the (at most two)
 // source columns of every destination pixel and combines the four values with OpenCV's resize weights.
+#include <stdlib.h>
+
 #include "tf_common.cuh"
 #include "farneback_internal.cuh"
 
@@ -62,38 +64,169 @@ __device__ __forceinline__ float byte_to_float(unsigned v, unsigned sel) {
     return __uint_as_float(__byte_perm(v, 0x4B000000u, sel)) - 8388608.f;
 }
 
-// pass A, 4 columns per thread (W % 4 == 0): one 32-bit load per tap row, float4 store
+// pass A, 4 columns per thread (W % 4 == 0): one 32-bit load per tap row, float4 store.  For a down-sampled level
+// (rp == 2) a thread produces both source rows of its destination row: they are neighbours (y1 == y0 + 1) except at the
+// bottom clamp, so one walk over ksize + 1 image rows feeds both accumulators (tap k of row y0 is tap k - 1 of row y1).
 __global__ void __launch_bounds__(256) blur_v4_kernel(const uint8_t* __restrict__ q0, const uint8_t* __restrict__ q1,
                                                       float* __restrict__ tmp, int H, int W, int h, int rp,
                                                       double scale_y, BlurTaps taps) {
     const int x4 = blockIdx.x * blockDim.x + threadIdx.x;   // group of 4 columns
-    const int r = blockIdx.y;
+    const int r = blockIdx.y;                               // source row (rp == 1) or destination row (rp == 2)
     const int img = blockIdx.z;
     const int W4 = W >> 2;
     if (x4 >= W4) return;
     const unsigned* src = reinterpret_cast<const unsigned*>(((img & 1) ? q1 : q0) + (long long)(img >> 1) * H * W);
-    int sy;
-    if (rp == 1) {
-        sy = r;
-    } else {
-        int y0, y1; float fy;
-        resize_coord(r >> 1, scale_y, H, y0, y1, fy);
-        sy = (r & 1) ? y1 : y0;
-    }
     const int rad = taps.ksize >> 1;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool interior = sy - rad >= 0 && sy + rad < H;
+    int y0 = r, y1 = r;
+    if (rp == 2) { float fy; resize_coord(r, scale_y, H, y0, y1, fy); }
+    float4* dst = reinterpret_cast<float4*>(tmp + ((long long)img * (h * rp) + (long long)r * rp) * W) + x4;
+    if (rp == 2 && y1 == y0 + 1 && y0 - rad >= 0 && y1 + rad < H) {
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        const unsigned* p = src + (long long)(y0 - rad) * W4 + x4;
+        float wprev = 0.f;
 #pragma unroll 4
-    for (int k = 0; k < taps.ksize; ++k) {
-        const int yy = interior ? sy + k - rad : reflect101(sy + k - rad, H);
-        const unsigned c = __ldg(src + yy * W4 + x4);
-        const float wk = taps.w[k];
-        acc.x += wk * byte_to_float(c, 0x7540u);
-        acc.y += wk * byte_to_float(c, 0x7541u);
-        acc.z += wk * byte_to_float(c, 0x7542u);
-        acc.w += wk * byte_to_float(c, 0x7543u);
+        for (int k = 0; k <= taps.ksize; ++k) {
+            const unsigned c = __ldg(p + (long long)k * W4);
+            const float wk = k < taps.ksize ? taps.w[k] : 0.f;
+            const float v0 = byte_to_float(c, 0x7540u), v1 = byte_to_float(c, 0x7541u);
+            const float v2 = byte_to_float(c, 0x7542u), v3 = byte_to_float(c, 0x7543u);
+            a0.x += wk * v0; a0.y += wk * v1; a0.z += wk * v2; a0.w += wk * v3;
+            a1.x += wprev * v0; a1.y += wprev * v1; a1.z += wprev * v2; a1.w += wprev * v3;
+            wprev = wk;
+        }
+        dst[0] = a0;
+        dst[W4] = a1;
+        return;
     }
-    reinterpret_cast<float4*>(tmp + ((long long)img * (h * rp) + r) * W)[x4] = acc;
+    for (int which = 0; which < rp; ++which) {
+        const int sy = which ? y1 : y0;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool interior = sy - rad >= 0 && sy + rad < H;
+#pragma unroll 4
+        for (int k = 0; k < taps.ksize; ++k) {
+            const int yy = interior ? sy + k - rad : reflect101(sy + k - rad, H);
+            const unsigned c = __ldg(src + (long long)yy * W4 + x4);
+            const float wk = taps.w[k];
+            acc.x += wk * byte_to_float(c, 0x7540u);
+            acc.y += wk * byte_to_float(c, 0x7541u);
+            acc.z += wk * byte_to_float(c, 0x7542u);
+            acc.w += wk * byte_to_float(c, 0x7543u);
+        }
+        dst[which * W4] = acc;
+    }
+}
+
+// Levels whose blur has 3 taps (the full-resolution level and the first half-resolution one) in ONE pass, straight from
+// the u8 image: no intermediate rows in HBM.  Same arithmetic as the two-pass path: vertical 3-tap sums first
+// (accumulated in tap order), then the horizontal ones, then OpenCV's bilinear resize weights.
+__device__ __forceinline__ float u8f(unsigned v) { return __uint_as_float(0x4B000000u | v) - 8388608.f; }
+
+// full resolution: 4 adjacent outputs per thread (W % 4 == 0)
+__global__ void __launch_bounds__(128) blur3_fullres_kernel(const uint8_t* __restrict__ q0, const uint8_t* __restrict__ q1,
+                                                            float* __restrict__ out, int H, int W, float w0, float w1,
+                                                            float w2) {
+    const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int img = blockIdx.z;
+    const int W4 = W >> 2;
+    if (x4 >= W4) return;
+    const uint8_t* src = ((img & 1) ? q1 : q0) + (long long)(img >> 1) * H * W;
+    const int xb = 4 * x4;
+    const int xl = reflect101(xb - 1, W), xr = reflect101(xb + 4, W);
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // vertical sums at columns xb-1 .. xb+4
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const uint8_t* row = src + (long long)reflect101(y + k - 1, H) * W;
+        const unsigned c = __ldg(reinterpret_cast<const unsigned*>(row) + x4);
+        const float wk = k == 0 ? w0 : (k == 1 ? w1 : w2);
+        v[0] += wk * u8f(__ldg(row + xl));
+        v[1] += wk * byte_to_float(c, 0x7540u);
+        v[2] += wk * byte_to_float(c, 0x7541u);
+        v[3] += wk * byte_to_float(c, 0x7542u);
+        v[4] += wk * byte_to_float(c, 0x7543u);
+        v[5] += wk * u8f(__ldg(row + xr));
+    }
+    float4 o;
+    o.x = (w0 * v[0] + w1 * v[1]) + w2 * v[2];
+    o.y = (w0 * v[1] + w1 * v[2]) + w2 * v[3];
+    o.z = (w0 * v[2] + w1 * v[3]) + w2 * v[4];
+    o.w = (w0 * v[3] + w1 * v[4]) + w2 * v[5];
+    reinterpret_cast<float4*>(out + ((long long)img * H + y) * W)[x4] = o;
+}
+
+// down-sampled level with a 3-tap blur: one output per thread from its 4 x 4 source footprint
+__global__ void __launch_bounds__(256) blur3_resize_kernel(const uint8_t* __restrict__ q0, const uint8_t* __restrict__ q1,
+                                                           float* __restrict__ out, int H, int W, int h, int w,
+                                                           double scale_x, double scale_y, float w0, float w1, float w2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int img = blockIdx.z;
+    if (i >= w) return;
+    const uint8_t* src = ((img & 1) ? q1 : q0) + (long long)(img >> 1) * H * W;
+    int x0, x1, y0, y1; float fx, fy;
+    resize_coord(i, scale_x, W, x0, x1, fx);
+    resize_coord(j, scale_y, H, y0, y1, fy);
+    float b[2][2];
+    if (x1 == x0 + 1 && x0 >= 1 && x1 + 1 < W && y1 == y0 + 1 && y0 >= 1 && y1 + 1 < H) {
+        // interior: one 4 x 4 byte footprint feeds both rows and both columns
+        const uint8_t* p = src + (long long)(y0 - 1) * W + (x0 - 1);
+        float P[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) P[r][c] = u8f(__ldg(p + r * W + c));
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float V[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float a = 0.f;
+                a += w0 * P[r][c];
+                a += w1 * P[r + 1][c];
+                a += w2 * P[r + 2][c];
+                V[c] = a;
+            }
+            float s0 = 0.f, s1 = 0.f;
+            s0 += w0 * V[0]; s0 += w1 * V[1]; s0 += w2 * V[2];
+            s1 += w0 * V[1]; s1 += w1 * V[2]; s1 += w2 * V[3];
+            b[r][0] = s0;
+            b[r][1] = s1;
+        }
+    } else {
+    // vertical sums of the two source rows at the three columns around x0 and around x1
+    float va[2][3], vb[2][3];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int sy = r ? y1 : y0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { va[r][c] = 0.f; vb[r][c] = 0.f; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint8_t* row = src + (long long)reflect101(sy + k - 1, H) * W;
+            const float wk = k == 0 ? w0 : (k == 1 ? w1 : w2);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                va[r][c] += wk * u8f(__ldg(row + reflect101(x0 + c - 1, W)));
+                vb[r][c] += wk * u8f(__ldg(row + reflect101(x1 + c - 1, W)));
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float wk = k == 0 ? w0 : (k == 1 ? w1 : w2);
+            s0 += wk * va[r][k];
+            s1 += wk * vb[r][k];
+        }
+        b[r][0] = s0;
+        b[r][1] = s1;
+    }
+    }
+    const float r0 = b[0][0] * (1.f - fx) + b[0][1] * fx;
+    const float r1 = b[1][0] * (1.f - fx) + b[1][1] * fx;
+    out[((long long)img * h + j) * w + i] = r0 * (1.f - fy) + r1 * fy;
 }
 
 // pass B at the full-resolution level (w == W, no resize), 4 outputs per thread (W % 4 == 0)
@@ -227,15 +360,30 @@ int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int 
     const int rp = (h == H) ? 1 : 2;
     const double sx = (double)W / w, sy = (double)H / h;
     const int n_img = 2 * n_pairs;
-    LaunchTimer lt(KC_PYRAMID, (2.0 * H * W + 8.0 * h * w) * n_pairs, s, 2 * cdiv(n_img, 65534));
+    static const char* env_two_pass = getenv("TF_PYR_TWO_PASS");
+    const bool fused3 = ksize == 3 && !env_two_pass && ((h == H && w == W && W % 4 == 0) || rp == 2);
+    LaunchTimer lt(KC_PYRAMID, (2.0 * H * W + 8.0 * h * w) * n_pairs, s, (fused3 ? 1 : 2) * cdiv(n_img, 65534));
     for (int z0 = 0; z0 < n_img; z0 += 65534) {
         const int nz = min(n_img - z0, 65534);  // even, so image parity is preserved
         const uint8_t* a0 = q0 + (long long)(z0 / 2) * H * W;
         const uint8_t* a1 = q1 + (long long)(z0 / 2) * H * W;
         float* tz = tmp + (long long)z0 * h * rp * W;
+        if (fused3) {
+            float* o3 = out + (long long)z0 * h * w;
+            if (h == H && w == W && W % 4 == 0 && (((uintptr_t)a0 | (uintptr_t)a1) % 4 == 0) && (uintptr_t)o3 % 16 == 0) {
+                dim3 g(cdiv(W / 4, 128), H, nz);
+                blur3_fullres_kernel<<<g, 128, 0, s>>>(a0, a1, o3, H, W, taps.w[0], taps.w[1], taps.w[2]);
+                continue;
+            }
+            if (rp == 2) {
+                dim3 g(cdiv(w, 256), h, nz);
+                blur3_resize_kernel<<<g, 256, 0, s>>>(a0, a1, o3, H, W, h, w, sx, sy, taps.w[0], taps.w[1], taps.w[2]);
+                continue;
+            }
+        }
         const bool vec4 = (W % 4 == 0) && (((uintptr_t)a0 | (uintptr_t)a1) % 4 == 0) && ((uintptr_t)tz % 16 == 0);
         if (vec4) {
-            dim3 ga(cdiv(W / 4, 128), h * rp, nz);
+            dim3 ga(cdiv(W / 4, 128), h, nz);
             blur_v4_kernel<<<ga, 128, 0, s>>>(a0, a1, tz, H, W, h, rp, sy, taps);
         } else {
             dim3 ga(cdiv(W, 256), h * rp, nz);
