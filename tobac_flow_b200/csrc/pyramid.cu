@@ -316,28 +316,45 @@ __global__ void __launch_bounds__(256) blur_h_resize_kernel(const float* __restr
     out[((long long)img * h + j) * w + i] = res;
 }
 
-// K6: dst (n_fields, h, w, 2) = resize_linear(src (n_fields, sh, sw, 2)) * mul ; zero-fill when src == nullptr
+// K6: dst (n_fields, h, w, 2) = resize_linear(src (n_fields, sh, sw, 2)) * mul ; zero-fill when src == nullptr.
+// Two adjacent outputs per thread (one 16-byte store); the row coordinate is computed once per thread.
+__device__ __forceinline__ float2 upsample_one(const float2* __restrict__ r0, const float2* __restrict__ r1, int x0, int x1,
+                                               float fx, float fy, float mul) {
+    const float2 a = r0[x0], b = r0[x1];
+    const float2 c = r1[x0], d = r1[x1];
+    const float ax = a.x * (1.f - fx) + b.x * fx, ay = a.y * (1.f - fx) + b.y * fx;
+    const float cx = c.x * (1.f - fx) + d.x * fx, cy = c.y * (1.f - fx) + d.y * fx;
+    return make_float2((ax * (1.f - fy) + cx * fy) * mul, (ay * (1.f - fy) + cy * fy) * mul);
+}
+
 __global__ void __launch_bounds__(256) flow_upsample_kernel(const float2* __restrict__ src, float2* __restrict__ dst, int sh,
                                                             int sw, int h, int w, double scale_x, double scale_y,
                                                             float mul) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     const int j = blockIdx.y;
     const int f = blockIdx.z;
     if (i >= w) return;
-    float2 o = make_float2(0.f, 0.f);
+    float2 o0 = make_float2(0.f, 0.f), o1 = o0;
     if (src != nullptr) {
         int x0, x1, y0, y1; float fx, fy;
-        resize_coord(i, scale_x, sw, x0, x1, fx);
         resize_coord(j, scale_y, sh, y0, y1, fy);
         const float2* s = src + (long long)f * sh * sw;
-        const float2 a = s[(long long)y0 * sw + x0], b = s[(long long)y0 * sw + x1];
-        const float2 c = s[(long long)y1 * sw + x0], d = s[(long long)y1 * sw + x1];
-        const float ax = a.x * (1.f - fx) + b.x * fx, ay = a.y * (1.f - fx) + b.y * fx;
-        const float cx = c.x * (1.f - fx) + d.x * fx, cy = c.y * (1.f - fx) + d.y * fx;
-        o.x = (ax * (1.f - fy) + cx * fy) * mul;
-        o.y = (ay * (1.f - fy) + cy * fy) * mul;
+        const float2* r0 = s + (long long)y0 * sw;
+        const float2* r1 = s + (long long)y1 * sw;
+        resize_coord(i, scale_x, sw, x0, x1, fx);
+        o0 = upsample_one(r0, r1, x0, x1, fx, fy, mul);
+        if (i + 1 < w) {
+            resize_coord(i + 1, scale_x, sw, x0, x1, fx);
+            o1 = upsample_one(r0, r1, x0, x1, fx, fy, mul);
+        }
     }
-    dst[((long long)f * h + j) * w + i] = o;
+    float2* d = dst + ((long long)f * h + j) * w + i;
+    if (i + 1 < w && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+        *reinterpret_cast<float4*>(d) = make_float4(o0.x, o0.y, o1.x, o1.y);
+    } else {
+        d[0] = o0;
+        if (i + 1 < w) d[1] = o1;
+    }
 }
 
 int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int H, int W, int h, int w, int ksize,
@@ -407,7 +424,7 @@ int launch_flow_upsample(const float* src, float* dst, int n_fields, int sh, int
     LaunchTimer lt(KC_UPSAMPLE, (8.0 * h * w + 8.0 * sh * sw) * n_fields, s, cdiv(n_fields, 65535));
     for (int z0 = 0; z0 < n_fields; z0 += 65535) {
         const int nz = min(n_fields - z0, 65535);
-        dim3 g(cdiv(w, 256), h, nz);
+        dim3 g(cdiv(cdiv(w, 2), 256), h, nz);
         flow_upsample_kernel<<<g, 256, 0, s>>>(
             src ? reinterpret_cast<const float2*>(src) + (long long)z0 * sh * sw : nullptr,
             reinterpret_cast<float2*>(dst) + (long long)z0 * h * w, sh, sw, h, w, sx, sy, mul);
