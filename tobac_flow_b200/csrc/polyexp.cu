@@ -27,11 +27,20 @@ __global__ void __launch_bounds__(256) polyexp_kernel(const float* __restrict__ 
     const int tid = threadIdx.x;
 
     // tile + 5-px halo, replicate-clamped (the clamp IS OpenCV's border rule for both passes)
-    for (int idx = tid; idx < PE_SH * PE_SW; idx += 256) {
-        const int r = idx / PE_SW, c = idx - r * PE_SW;
-        const int gy = min(max(y0 + r - PE_N, 0), h - 1);
+    // (all 21 loads of a thread are issued before the first shared-memory store: one memory round trip, not 21)
+    {
+        static_assert((PE_SH * PE_SW) % 256 == 0 && PE_SW == 128, "tile load: 2 rows per pass of the 256 threads");
+        constexpr int PASSES = PE_SH * PE_SW / 256;
+        const int c = tid & (PE_SW - 1), r0 = tid >> 7;
         const int gx = min(max(x0 + c - PE_N, 0), w - 1);
-        s_in[r][c] = src[gy * w + gx];
+        float v[PASSES];
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+            const int gy = min(max(y0 + r0 + 2 * p - PE_N, 0), h - 1);
+            v[p] = __ldg(src + gy * w + gx);
+        }
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) s_in[r0 + 2 * p][c] = v[p];
     }
     __syncthreads();
 
