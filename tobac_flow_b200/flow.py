@@ -354,12 +354,17 @@ class Flow:
             return host.numpy()
         fwd, bwd = self.forward_flow_device, self.backward_flow_device
         per_frame = H * W * out_t.itemsize * (n_taps if stack else 1)
-        Tc = max(1, min(T, _HOST_CHUNK_BYTES // max(per_frame, 1)))
+        # chunks of at most _HOST_CHUNK_BYTES of result, and at least four of them so that upload, kernels and download
+        # of neighbouring chunks overlap even for the small results (diff)
+        Tc = max(1, min(T, _HOST_CHUNK_BYTES // max(per_frame, 1), -(-T // 4)))
         chunks = [(a0, min(a0 + Tc, T)) for a0 in range(0, T, Tc)]
         cur = torch.cuda.current_stream()
         s_in, s_out = _side_streams(dev)
-        d_in = torch.empty((T, H, W), dtype=src.dtype, device=dev)
-        s_in.wait_stream(cur)
+        # the operand buffer belongs to the upload stream's pool, so the copies need not wait for the work already queued
+        # on the current stream (typically the flow kernels of the create_flow call just before): they run underneath it
+        with torch.cuda.stream(s_in):
+            d_in = torch.empty((T, H, W), dtype=src.dtype, device=dev)
+        d_in.record_stream(cur)
         s_out.wait_stream(cur)
         ev_in = []
         with torch.cuda.stream(s_in):
