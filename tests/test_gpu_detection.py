@@ -265,3 +265,25 @@ def test_get_anvil_markers(multi):
         got = get_anvil_markers(flow, wvd, threshold=thr, overlap=ov, absolute_overlap=ab, min_length=ml)
         assert np.array_equal(got, want), (thr, ov, ab, ml)
     assert det.get_anvil_markers(wvd, fwd, bwd, backend=BACKEND).max() >= 1
+
+
+def test_short_and_degenerate_series():
+    """One- and two-frame series, tiny frames, all-true / all-false masks: same answers as the oracle, no crashes."""
+    import tobac_flow_b200 as tfb
+    from tobac_flow_b200.detection import growth_markers_device
+    rng = np.random.default_rng(2)
+    for T, H, W in ((1, 20, 30), (2, 9, 7), (3, 33, 65)):
+        fwd = (rng.standard_normal((T, H, W, 2)) * 0.7).astype(np.float32)
+        bwd = (rng.standard_normal((T, H, W, 2)) * 0.7).astype(np.float32)
+        flow = tfb.Flow(fwd, bwd)
+        for mask in (rng.random((T, H, W)) < 0.4, np.ones((T, H, W), bool), np.zeros((T, H, W), bool)):
+            want = det.flow_label(mask, fwd, bwd, absolute_overlap=1, backend=BACKEND)
+            assert np.array_equal(flow.label(mask), want), (T, H, W)
+        if T >= 2:
+            wvd = (rng.standard_normal((T, H, W)) * 8 - 10).astype(np.float32)
+            dt = np.full(T, 5.0)
+            r = growth_markers_device(flow, torch.from_numpy(wvd).cuda(), dt)
+            want = det.detect_growth_markers(wvd, dt, fwd, bwd, backend=BACKEND, intermediates=True)
+            assert np.array_equal(r["smoothed"].cpu().numpy(), want["smoothed"], equal_nan=True)
+            assert np.array_equal(r["seeds"].cpu().numpy().astype(bool), want["seeds"])
+            assert np.array_equal(r["markers"].cpu().numpy(), want["markers"])

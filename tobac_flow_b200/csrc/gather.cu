@@ -200,12 +200,9 @@ struct RedStat {  // nanmean / nanmax / nanmin / any
 // KT: type the taps are kept in = the narrower of operand and stack dtype (the cast to ST is then exact and is redone on use)
 template <typename ST, typename KT>
 struct RedSobel {
-    int dir; ST centre; KT v[27]; bool any_nan;
-    __device__ __forceinline__ void init(int d, ST c) { dir = d; centre = c; any_nan = false; }
-    __device__ __forceinline__ void add(int, int k, KT val) {
-        v[k] = val;
-        any_nan |= is_nan(val);
-    }
+    int dir; ST centre; KT v[27];
+    __device__ __forceinline__ void init(int d, ST c) { dir = d; centre = c; }
+    __device__ __forceinline__ void add(int, int k, KT val) { v[k] = val; }
     // general form: d_k = v_k - centre (optionally clipped), NaN terms skipped, fp64 sums of d_k * S_k
     __device__ __forceinline__ ST finish_general() const {
         double gx = 0.0, gy = 0.0, gt = 0.0;
@@ -247,8 +244,18 @@ struct RedSobel {
         const double gt = gts[2] - gts[0];
         return sqrt(gx * gx + gy * gy + gt * gt);
     }
+    // plain direction, fp64: the separable form when no tap is NaN, else the general form (which skips NaN taps).  Every
+    // non-centre tap has a non-zero weight in at least one gradient, so a finite separable result proves that no such
+    // tap is NaN and the 27 NaN tests are only made when the result is not finite; the centre tap is tested directly.
     __device__ __forceinline__ ST finish() const {
-        if (sizeof(ST) == 8 && dir == TF_RED_SOBEL && !any_nan) return (ST)finish_separable();
+        if (sizeof(ST) == 8 && dir == TF_RED_SOBEL) {
+            const double r = finish_separable();
+            if (isfinite(r) && !is_nan(v[13])) return (ST)r;
+            bool any_nan = false;
+#pragma unroll
+            for (int k = 0; k < 27; ++k) any_nan |= is_nan(v[k]);
+            if (!any_nan) return (ST)r;
+        }
         return finish_general();
     }
 };
@@ -342,12 +349,22 @@ __global__ void __launch_bounds__(256) sl_gather_kernel(GatherArgs a) {
         SrcT tapv[9];
         bool oob1[9];
         if (slab == 1) {
+            if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
+                const SrcT* c0 = cur + pix - W - 1;      // interior: no tap leaves the image
 #pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                if (!((bits >> j) & 1u)) continue;
-                const int yy = y + j / 3 - 1, xx = x + j % 3 - 1;
-                oob1[j] = !((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W);
-                tapv[j] = oob1[j] ? fill_s : cur[yy * W + xx];
+                for (int j = 0; j < 9; ++j) {
+                    if (!((bits >> j) & 1u)) continue;
+                    oob1[j] = false;
+                    tapv[j] = c0[(j / 3) * W + (j % 3)];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    if (!((bits >> j) & 1u)) continue;
+                    const int yy = y + j / 3 - 1, xx = x + j % 3 - 1;
+                    oob1[j] = !((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W);
+                    tapv[j] = oob1[j] ? fill_s : cur[yy * W + xx];
+                }
             }
         } else {
             bool have_patch = false;
