@@ -17,8 +17,11 @@
 //     stores the new flow (32 B per thread, coalesced).
 //   * forward and backward CTAs of the same pair and strip are adjacent in launch order, so the second reader of the
 //     shared R planes hits L2.
-//   * work distribution (default, TF_PERSIST=0 restores the chunk grid): all (pair, strip) columns are laid end to end
-//     and one resident wave of forward/backward CTA pairs takes equal spans of that row space (measured +2 %).
+//   * work distribution: a grid of (strip, row chunk, pair) CTAs, the chunk count chosen to minimise waves x rows.
+//     TF_PERSIST=1 selects the measured alternative: all (pair, strip) columns laid end to end and one resident wave of
+//     forward/backward CTA pairs taking equal spans of that row space.  It saves warm-up rows and the tail (+2 % with
+//     equal code), but its column loop costs the row loop 28 bytes of spills and the spill-free chunk grid is 4 %
+//     faster (276 vs 289 ms per CONUS day at the full-resolution level), so the chunk grid is the default.
 // Measured and rejected: pulling the strip's next rows into L2 ahead of the march, either with five
 // cp.async.bulk.prefetch.L2 per row or with one prefetch.global.L2 per 128-byte line from warp 0, 4-16 rows ahead
 // (117-134 ms vs 95 ms: the extra work of one warp delays the whole CTA at the batch barrier); two rows of taps in flight per thread (168 registers, 3 CTAs/SM: 126-144 ms vs 94.5 ms; a warp
@@ -171,11 +174,14 @@ __device__ __forceinline__ float diff_of_products(float a, float b, float c, flo
     return dop + err;
 }
 
-template <int NT, int HK, bool HS>
+// PS (persistent) selects the work distribution at compile time: the chunk-grid instantiation carries none of the
+// column loop's state (it needs the 128-register budget to itself; the persistent one spills 28 bytes).
+template <int NT, int HK, bool HS, bool PS>
 __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : (HS ? TF_HS_CTAS : 4)))
 fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const float* __restrict__ flow_in,
                      float* __restrict__ out_fwd, long long fwd_stride, float* __restrict__ out_bwd,
-                     long long bwd_stride, int h, int w, int chunk_rows, float clampv, int strips, int span, int total) {
+                     long long bwd_stride, int h, int w, int chunk_rows, float clampv, int strips, int span_arg, int total) {
+    const int span = PS ? span_arg : 0;
     using C = StripCfg<NT, HK, HS>;
     extern __shared__ __align__(16) float smem[];
     float* ring = smem;                       // [batch % 3][P0..P2][k][col]: prefix sums of the batch's rows
@@ -389,13 +395,14 @@ static void launch_strip(const float* R, long long img_stride, const float* flow
     using C = StripCfg<NT, HK, HS>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(fb_iter_strip_kernel<NT, HK, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        cudaFuncSetAttribute(fb_iter_strip_kernel<NT, HK, HS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        cudaFuncSetAttribute(fb_iter_strip_kernel<NT, HK, HS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         attr_set = true;
     }
     const int strips = cdiv(w, C::OUT_W);
     const long long slots = 148LL * (NT == 256 ? 2 : (HS ? TF_HS_CTAS : 4));
     static const char* env_persist = getenv("TF_PERSIST");
-    const bool persist = env_persist ? atoi(env_persist) != 0 : true;
+    const bool persist = env_persist ? atoi(env_persist) != 0 : false;
     const long long total = (long long)n_pairs * strips * h;
     static const char* env_min = getenv("TF_PERSIST_MIN_ROWS");
     const long long min_rows = env_min ? atoll(env_min) : 128;   // below this the chunk grid's extra parallelism wins
@@ -404,7 +411,7 @@ static void launch_strip(const float* R, long long img_stride, const float* flow
         // CTA still gets at least 24 rows so the warm-up rows do not dominate
         const int span = (int)max((total + slots / 2 - 1) / (slots / 2), 24LL);
         const int n_cta_pairs = (int)((total + span - 1) / span);
-        fb_iter_strip_kernel<NT, HK, HS><<<2 * n_cta_pairs, NT, C::SMEM_BYTES, s>>>(
+        fb_iter_strip_kernel<NT, HK, HS, true><<<2 * n_cta_pairs, NT, C::SMEM_BYTES, s>>>(
             R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, h, w, 0, clamp, strips, span, (int)total);
         return;
     }
@@ -421,7 +428,7 @@ static void launch_strip(const float* R, long long img_stride, const float* flow
     for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
         const int np = min(n_pairs - p0, 65535);
         dim3 g(2 * strips, chunks, np);
-        fb_iter_strip_kernel<NT, HK, HS><<<g, NT, C::SMEM_BYTES, s>>>(R + (long long)(2 * p0) * img_stride, img_stride,
+        fb_iter_strip_kernel<NT, HK, HS, false><<<g, NT, C::SMEM_BYTES, s>>>(R + (long long)(2 * p0) * img_stride, img_stride,
                                                               flow_in + (long long)(2 * p0) * 2 * h * w,
                                                               out_fwd + p0 * fwd_stride, fwd_stride,
                                                               out_bwd + p0 * bwd_stride, bwd_stride, h, w, chunk_rows, clamp,
