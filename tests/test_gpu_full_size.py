@@ -93,3 +93,24 @@ def test_full_disk_pair_vs_opencv_and_batch_independence(tfb, shape):
     assert np.array_equal(g.backward_flow[1], f.backward_flow[1]) and np.array_equal(g.backward_flow[3], f.backward_flow[1])
     del f, g
     torch.cuda.empty_cache()
+
+
+def test_conus_growth_markers_vs_oracle(tfb):
+    """detect_growth_markers on four CONUS-size frames with the library's own flow: every intermediate and the marker
+    labels identical to the oracle (scipy.ndimage + OpenCV remap on the host) fed the same flow."""
+    import torch
+    from oracle import detection_ops as det
+    from tobac_flow_b200.detection import growth_markers_device
+    T = 4
+    bt = synthetic.bt_sequence(T + 8, 1500, 2500, seed=1236, nans=True)[6:6 + T]   # frames in which cores are growing
+    wvd = synthetic.wvd_from_bt(bt).astype(np.float32)
+    flow = tfb.create_flow(bt)
+    dt = np.full(T, 5.0)
+    r = growth_markers_device(flow, torch.from_numpy(wvd).cuda(), dt)
+    want = det.detect_growth_markers(wvd, dt, flow.forward_flow, flow.backward_flow, backend=BACKEND, intermediates=True)
+    assert np.array_equal(r["smoothed"].cpu().numpy(), want["smoothed"], equal_nan=True)
+    assert np.array_equal(r["filtered"].cpu().numpy(), want["filtered"], equal_nan=True)
+    assert np.array_equal(r["seeds"].cpu().numpy().astype(bool), want["seeds"])
+    assert np.array_equal(r["linked"].cpu().numpy(), want["linked"])
+    assert np.array_equal(r["markers"].cpu().numpy(), want["markers"])
+    assert want["linked"].max() > 10
