@@ -22,7 +22,8 @@
 //     forward/backward CTA pairs taking equal spans of that row space.  It saves warm-up rows and the tail (+2 % with
 //     equal code), but its column loop costs the row loop 28 bytes of spills and the spill-free chunk grid is 4 %
 //     faster (276 vs 289 ms per CONUS day at the full-resolution level), so the chunk grid is the default.
-// Measured and rejected: pulling the strip's next rows into L2 ahead of the march, either with five
+// Measured and rejected: loading R0 about two rows ahead in place of one (equal: 91.5 vs 91.1 ms); pulling the strip's
+// next rows into L2 ahead of the march, either with five
 // cp.async.bulk.prefetch.L2 per row or with one prefetch.global.L2 per 128-byte line from warp 0, 4-16 rows ahead
 // (117-134 ms vs 95 ms: the extra work of one warp delays the whole CTA at the batch barrier); two rows of taps in flight per thread (168 registers, 3 CTAs/SM: 126-144 ms vs 94.5 ms; a warp
 // has six scoreboards, already taken by cur / next taps, the flow queue and the shared-memory reads); inheriting a row's top taps from the previous row's bottom taps (per-lane predicated loads,
