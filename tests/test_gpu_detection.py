@@ -287,3 +287,16 @@ def test_short_and_degenerate_series():
             assert np.array_equal(r["smoothed"].cpu().numpy(), want["smoothed"], equal_nan=True)
             assert np.array_equal(r["seeds"].cpu().numpy().astype(bool), want["seeds"])
             assert np.array_equal(r["markers"].cpu().numpy(), want["markers"])
+
+
+def test_sharded_label_single_rank_cuda_backend(multi):
+    """ShardedFlow.label with the CUDA back-end on one rank (the collectives are skipped at world size 1; they are
+    covered by the gloo tests and by scratch/label_sharded_check.py under torchrun)."""
+    from tobac_flow_b200 import distributed as D
+    g, wvd, fwd, bwd, flow = multi
+    seeds = unpack(g["seeds"], wvd.shape)
+    fl = D.ShardedFlow(torch.from_numpy(fwd).cuda(), torch.from_numpy(bwd).cuda(), 0, 1)
+    lab = fl.label(torch.from_numpy(seeds).cuda())
+    assert np.array_equal(lab.cpu().numpy(), g["linked"])
+    lab = fl.label(torch.from_numpy(seeds).cuda(), overlap=0.5, absolute_overlap=4)
+    assert np.array_equal(lab.cpu().numpy(), g["linked_ov"])

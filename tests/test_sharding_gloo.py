@@ -51,6 +51,90 @@ class OracleOps:
         return torch.from_numpy(np.stack(res))
 
 
+    # -- labelling back-end: scipy / numpy / the oracle's nearest-neighbour gather -----------------------------------
+    def flat_label(self, mask_u8, connectivity):
+        from oracle import detection_ops as det
+        from scipy import ndimage as ndi
+        s = ndi.generate_binary_structure(3, 1) if connectivity == 1 else np.ones((3, 3, 3), bool)
+        lab = det.flat_label(mask_u8.numpy() != 0, s)
+        return torch.from_numpy(lab.astype(np.int32)), int(lab.max())
+
+    def overlap_table(self, flat_view, fwd, bwd, label_struct, has_prev, has_next, n_labels):
+        d = flat_view.numpy()
+        n = d.shape[0] - int(has_prev) - int(has_next)
+        keys, counts = [], []
+        local = d[int(has_prev):int(has_prev) + n]
+        back = np.zeros_like(local)
+        forw = np.zeros_like(local)
+        for i in range(n):
+            j = i + int(has_prev)
+            blank = np.zeros(d[j].shape, np.int32)
+            prev = d[j - 1] if j > 0 else blank
+            nxt = d[j + 1] if j < d.shape[0] - 1 else blank
+            back[i] = ops.warp_image(prev, bwd[i].numpy(), "nearest", 0, 0, 0, "numpy")
+            forw[i] = ops.warp_image(nxt, fwd[i].numpy(), "nearest", 0, 0, 0, "numpy")
+        for direction, nb in ((0, forw), (1, back)):
+            sel = (local > 0) & (nb > 0)
+            k = (np.uint64(direction) << np.uint64(62)) | (local[sel].astype(np.uint64) << np.uint64(31)) | nb[sel].astype(np.uint64)
+            u, c = np.unique(k, return_counts=True)
+            keys.append(u)
+            counts.append(c.astype(np.int32))
+        sizes = np.bincount(local.ravel(), minlength=n_labels + 1).astype(np.int32)
+        sizes[0] = 0
+        return np.concatenate(keys), np.concatenate(counts), sizes
+
+    def relabel(self, flat, mapping):
+        return torch.from_numpy(mapping[flat.numpy()].astype(np.int32))
+
+
+def _label_case():
+    """Masks of a drifting blob field plus the flow that advects it (so labels link across frames and shards)."""
+    from scipy import ndimage as ndi
+    rng = np.random.default_rng(31)
+    base = ndi.gaussian_filter(rng.standard_normal((H + 30, W + 30)), 2.0)
+    mask = np.stack([np.roll(base, (t, 2 * t), (0, 1))[15:15 + H, 15:15 + W] > 0.03 for t in range(T)])
+    mask[3, 10:20] = False
+    fwd = (rng.standard_normal((T, H, W, 2)) * 0.2 + np.array([2.0, 1.0])).astype(np.float32)
+    bwd = (rng.standard_normal((T, H, W, 2)) * 0.2 - np.array([2.0, 1.0])).astype(np.float32)
+    return mask, fwd, bwd
+
+
+def _label_worker(rank, world, port, q, overlap, absolute):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mask, fwd, bwd = _label_case()
+        t0, t1 = D.shard_bounds(T, world, rank)
+        fl = D.ShardedFlow(torch.from_numpy(fwd[t0:t1].copy()), torch.from_numpy(bwd[t0:t1].copy()), rank, world,
+                           ops=OracleOps())
+        lab = fl.label(torch.from_numpy(mask[t0:t1].copy()), overlap=overlap, absolute_overlap=absolute)
+        q.put((rank, t0, t1, lab.numpy().copy()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,overlap,absolute", [(2, 0.0, 1), (3, 0.0, 1), (3, 0.4, 3)])
+def test_sharded_label_equals_unsharded(world, overlap, absolute):
+    from oracle import detection_ops as det
+    mask, fwd, bwd = _label_case()
+    want = det.flow_label(mask, fwd, bwd, overlap=overlap, absolute_overlap=absolute)
+    assert want.max() >= 3 and len(np.unique(want[0])) > 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_label_worker, args=(r, world, port, q, overlap, absolute)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, t0, t1, lab in got:
+        assert np.array_equal(lab, want[t0:t1]), rank
+
+
 def _data():
     bt = synthetic.bt_sequence(T, H, W, seed=77, nans=False)
     bt[3, 5:8, 10:20] = np.nan

@@ -10,7 +10,10 @@ exchange over NCCL point-to-point (NVLink):
 * one flow field (8*H*W bytes): the pair ``(t1-1, t1)`` computed on rank r yields ``backward_flow[t1]``, which
   belongs to rank r+1.
 
-No collective is involved; the sequence end rules (``flow.py:425-426``) apply on the first / last rank only.
+No collective is involved in the flow / stencil path; the sequence end rules (``flow.py:425-426``) apply on the
+first / last rank only.  ``ShardedFlow.label`` (the semi-Lagrangian labelling of a sharded mask) is the one operator
+with a real exchange step: per-rank component counts, per-label pixel counts and the (label, neighbour, overlap)
+tables are gathered (a few thousand entries) so that every rank can run the same linking walk.
 The compute back-end is injectable so the sharding logic can be exercised on CPU with ``gloo`` (tests).
 """
 from dataclasses import dataclass
@@ -39,6 +42,25 @@ class CudaOps:
     def convolve(self, data, fwd, bwd, structure, method, fill_value, dtype, reducer, has_prev, has_next, out=None):
         from .flow import convolve_device
         return convolve_device(data, fwd, bwd, structure, method, fill_value, dtype, reducer, has_prev, has_next, out)
+
+    # -- labelling (flow_label on a time-sharded mask) --------------------------------------------------------------
+    def flat_label(self, mask_u8, connectivity):
+        from .label import flat_label_device
+        return flat_label_device(mask_u8, connectivity)
+
+    def overlap_table(self, flat_view, fwd, bwd, label_struct, has_prev, has_next, n_labels):
+        """(keys, counts, sizes) of this rank's frames; ``flat_view`` carries the halo frames that exist."""
+        from . import _lib
+        from .flow import convolve_device
+        from .label import overlap_table_device
+        taps = convolve_device(flat_view, fwd, bwd, label_struct, "nearest", 0, np.int32, _lib.TF_RED_NONE,
+                               has_prev, has_next)
+        local = flat_view[int(has_prev):flat_view.shape[0] - int(has_next)].contiguous()
+        return overlap_table_device(local, taps[0], taps[1], n_labels)
+
+    def relabel(self, flat, mapping):
+        from .label import relabel_device
+        return relabel_device(flat, mapping)
 
 
 def _p2p(ops, group):
@@ -109,6 +131,57 @@ class ShardedFlow:
             shard.exchange_halos(self.group)
         return self.ops.convolve(shard.stencil_view(), self.fwd, self.bwd, structure, method, fill_value, dtype,
                                  reducer, shard.has_prev, shard.has_next, out)
+
+    def label(self, mask_local, structure=None, overlap: float = 0.0, absolute_overlap: int = 1):
+        """``Flow.label`` (tobac_flow/flow.py:281-330 -> label.py:84-175) on a time-sharded mask: every rank passes the
+        (T_loc, H, W) mask of its own frames and gets the labels of those frames, numbered exactly as the unsharded
+        call numbers them.
+
+        Per-frame components are local.  The exchange steps are: an all-gather of the per-rank component counts (the
+        global numbering continues from rank to rank, as scipy's does from frame to frame), the one-frame halos of the
+        numbered components (point to point), a sum of the per-label pixel counts and an all-gather of the
+        (label, neighbour, overlap) tables; a few thousand entries each.  The order-dependent linking walk then runs
+        redundantly on every rank, so no label map has to be broadcast."""
+        from .label import _connectivity, _default_structure, _label_struct, link_groups_host
+        if structure is None:
+            structure = _default_structure()
+        dev = mask_local.device
+        m = (mask_local != 0).to(torch.uint8).contiguous()
+        flat, n_loc = self.ops.flat_label(m, _connectivity(structure))
+        flat = flat.to(torch.int32)
+        if self.world > 1:
+            counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(self.world)]
+            dist.all_gather(counts, torch.tensor([n_loc], dtype=torch.int64, device=dev), group=self.group)
+            counts = [int(c.item()) for c in counts]
+        else:
+            counts = [int(n_loc)]
+        offset, total = sum(counts[:self.rank]), sum(counts)
+        if offset:
+            flat = flat + (flat > 0).to(torch.int32) * offset
+        shard = make_shard(flat, self.rank, self.world)
+        shard.buf[0] = 0
+        shard.buf[-1] = 0
+        shard.exchange_halos(self.group)
+        keys, cnts, sizes = self.ops.overlap_table(shard.stencil_view(), self.fwd, self.bwd, _label_struct(structure),
+                                                   shard.has_prev, shard.has_next, total)
+        if self.world > 1:
+            sz = torch.from_numpy(np.ascontiguousarray(sizes, dtype=np.int64)).to(dev)
+            dist.all_reduce(sz, op=dist.ReduceOp.SUM, group=self.group)
+            sizes = sz.cpu().numpy().astype(np.int32)
+            n_e = torch.tensor([len(keys)], dtype=torch.int64, device=dev)
+            lens = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(self.world)]
+            dist.all_gather(lens, n_e, group=self.group)
+            lens = [int(v.item()) for v in lens]
+            pad = max(max(lens), 1)
+            table = torch.zeros((2, pad), dtype=torch.int64, device=dev)
+            table[0, :len(keys)] = torch.from_numpy(keys.view(np.int64)).to(dev)
+            table[1, :len(keys)] = torch.from_numpy(cnts.astype(np.int64)).to(dev)
+            tables = [torch.zeros_like(table) for _ in range(self.world)]
+            dist.all_gather(tables, table, group=self.group)
+            keys = np.concatenate([t[0, :n].cpu().numpy().view(np.uint64) for t, n in zip(tables, lens)])
+            cnts = np.concatenate([t[1, :n].cpu().numpy().astype(np.int32) for t, n in zip(tables, lens)])
+        mapping, _ = link_groups_host(keys, cnts, sizes, total, overlap, absolute_overlap)
+        return self.ops.relabel(shard.local.contiguous(), mapping)
 
 
 def create_flow_sharded(shard: Shard, smoothing_passes=0, interp_method="linear", max_value=20, ops=None, group=None,

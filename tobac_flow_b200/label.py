@@ -89,24 +89,13 @@ def _label_struct(structure):
     return label_struct
 
 
-def link_overlap_device(flow, flat: torch.Tensor, structure, overlap: float, absolute_overlap: int,
-                        n_labels: int | None = None) -> tuple[torch.Tensor, int]:
-    """The body shared by ``flow_label`` and ``flow_link_overlap`` on an int32 CUDA tensor of flat labels."""
+def overlap_table_device(flat: torch.Tensor, back: torch.Tensor, fwd: torch.Tensor, n_labels: int):
+    """tf_label_overlap_count on int32 CUDA tensors -> host arrays (keys uint64, counts int32, sizes int32[n_labels+1]):
+    the (direction, label, neighbour) overlap histogram of ``flat`` against its two warped neighbours and
+    np.bincount(flat).  Labels may be any values in 0..n_labels (a time shard holds a sub-range of them)."""
     lib = _lib.load()
     dev = flat.device
     n = flat.numel()
-    out = torch.zeros_like(flat)
-    if n == 0:
-        return out, 0
-    if n_labels is None:
-        mx = torch.zeros((1,), dtype=torch.int32, device=dev)
-        _lib.check(lib.tf_label_max(flat.data_ptr(), n, mx.data_ptr(), _stream()), "tf_label_max")
-        n_labels = int(mx.item())
-        if bool((flat < 0).any()):
-            raise ValueError("flat labels must be non-negative")                      # np.bincount raises the same
-    taps = convolve_device(flat, flow.forward_flow_device, flow.backward_flow_device, _label_struct(structure),
-                           "nearest", 0, np.int32, _lib.TF_RED_NONE)
-    back, fwd = taps[0], taps[1]
     sizes = torch.empty((n_labels + 1,), dtype=torch.int32, device=dev)
     flags = torch.empty((2,), dtype=torch.int32, device=dev)
     cap = 1024
@@ -125,18 +114,55 @@ def link_overlap_device(flow, flat: torch.Tensor, structure, overlap: float, abs
             break
         cap *= 4                                                                     # table overflow: retry larger
     used = keys != -1
-    k_h = keys[used].cpu().numpy().view(np.uint64)
-    c_h = counts[used].cpu().numpy()
-    s_h = sizes.cpu().numpy()
-    k_h = np.ascontiguousarray(k_h)
-    c_h = np.ascontiguousarray(c_h)
+    k_h = np.ascontiguousarray(keys[used].cpu().numpy().view(np.uint64))
+    c_h = np.ascontiguousarray(counts[used].cpu().numpy())
+    return k_h, c_h, sizes.cpu().numpy()
+
+
+def link_groups_host(keys: np.ndarray, counts: np.ndarray, sizes: np.ndarray, n_labels: int, overlap: float,
+                     absolute_overlap: int):
+    """tf_label_link_groups (the order-dependent walk of label.py:139-163, run on the host inside the library) ->
+    (relabel table int32[n_labels+1], number of linked objects)."""
+    lib = _lib.load()
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    sizes = np.ascontiguousarray(sizes, dtype=np.int32)
     mapping = np.zeros(n_labels + 1, np.int32)
-    n_obj = lib.tf_label_link_groups(k_h.ctypes.data, c_h.ctypes.data, len(k_h), s_h.ctypes.data, n_labels,
+    n_obj = lib.tf_label_link_groups(keys.ctypes.data, counts.ctypes.data, len(keys), sizes.ctypes.data, n_labels,
                                      ctypes.c_double(float(overlap)), int(absolute_overlap), mapping.ctypes.data)
     _lib.check(min(n_obj, 0), "tf_label_link_groups")
-    map_d = torch.from_numpy(mapping).to(dev)
-    _lib.check(lib.tf_relabel(flat.data_ptr(), map_d.data_ptr(), out.data_ptr(), n, n_labels, _stream()), "tf_relabel")
-    return out, int(n_obj)
+    return mapping, int(n_obj)
+
+
+def relabel_device(flat: torch.Tensor, mapping: np.ndarray) -> torch.Tensor:
+    """out = mapping[flat] on the device (label.py:165-170)."""
+    out = torch.zeros_like(flat)
+    if flat.numel():
+        map_d = torch.from_numpy(np.ascontiguousarray(mapping, dtype=np.int32)).to(flat.device)
+        _lib.check(_lib.load().tf_relabel(flat.data_ptr(), map_d.data_ptr(), out.data_ptr(), flat.numel(),
+                                          len(mapping) - 1, _stream()), "tf_relabel")
+    return out
+
+
+def link_overlap_device(flow, flat: torch.Tensor, structure, overlap: float, absolute_overlap: int,
+                        n_labels: int | None = None) -> tuple[torch.Tensor, int]:
+    """The body shared by ``flow_label`` and ``flow_link_overlap`` on an int32 CUDA tensor of flat labels."""
+    lib = _lib.load()
+    dev = flat.device
+    n = flat.numel()
+    if n == 0:
+        return torch.zeros_like(flat), 0
+    if n_labels is None:
+        mx = torch.zeros((1,), dtype=torch.int32, device=dev)
+        _lib.check(lib.tf_label_max(flat.data_ptr(), n, mx.data_ptr(), _stream()), "tf_label_max")
+        n_labels = int(mx.item())
+        if bool((flat < 0).any()):
+            raise ValueError("flat labels must be non-negative")                      # np.bincount raises the same
+    taps = convolve_device(flat, flow.forward_flow_device, flow.backward_flow_device, _label_struct(structure),
+                           "nearest", 0, np.int32, _lib.TF_RED_NONE)
+    keys, counts, sizes = overlap_table_device(flat, taps[0], taps[1], n_labels)
+    mapping, n_obj = link_groups_host(keys, counts, sizes, n_labels, overlap, absolute_overlap)
+    return relabel_device(flat, mapping), n_obj
 
 
 def flow_label(flow, mask, structure=None, dtype: type = np.int32, overlap: float = 0.0, absolute_overlap: int = 0,
