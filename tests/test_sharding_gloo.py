@@ -45,7 +45,7 @@ class OracleOps:
             prev = d[j - 1] if j > 0 else blank
             nxt = d[j + 1] if j < d.shape[0] - 1 else blank
             stack = ops.tap_stack(prev, d[j], nxt, fwd[i].numpy(), bwd[i].numpy(), structure, method, dtype, fill_value)
-            r = ops.diff_reducer(stack).astype(dtype)
+            r = (ops.nanmean_reducer(stack) if reducer == 2 else ops.diff_reducer(stack)).astype(dtype)
             r[np.isnan(d[j])] = fill_value
             res.append(r)
         return torch.from_numpy(np.stack(res))
@@ -85,6 +85,35 @@ class OracleOps:
 
     def relabel(self, flat, mapping):
         return torch.from_numpy(mapping[flat.numpy()].astype(np.int32))
+
+    # -- detection back-end: scipy.ndimage, as the reference calls it --------------------------------------------------
+    def scale_frames(self, raw32, dt_minutes):
+        return torch.from_numpy(raw32.numpy() / np.asarray(dt_minutes, np.float64)[:, None, None])
+
+    def growth_seed_masks(self, smoothed, wvd):
+        from oracle import detection_ops as det
+        from scipy import ndimage as ndi
+        s2 = ndi.generate_binary_structure(2, 1)[np.newaxis, ...]
+        filtered = ndi.grey_opening(smoothed.numpy(), footprint=s2) * det.get_curvature_filter(wvd.numpy())
+        seeds = ndi.binary_opening(filtered >= 0.25, structure=s2)
+        as_u8 = lambda a: torch.from_numpy(a.astype(np.uint8))
+        return as_u8(filtered >= 0.5), as_u8(wvd.numpy() >= -5), as_u8(seeds)
+
+    def label_stats(self, labels, mask_a, mask_b, n_labels):
+        lab, a, b = labels.numpy(), mask_a.numpy() != 0, mask_b.numpy() != 0
+        tmin = np.full(n_labels + 1, 0x7f7f7f7f, np.int32)
+        tmax = np.full(n_labels + 1, -1, np.int32)
+        any_a = np.zeros(n_labels + 1, np.int32)
+        any_b = np.zeros(n_labels + 1, np.int32)
+        for t in range(lab.shape[0]):
+            for l in np.unique(lab[t]):
+                if l > 0:
+                    tmin[l] = min(tmin[l], t)
+                    tmax[l] = max(tmax[l], t)
+        any_a[np.unique(lab[a])] = 1
+        any_b[np.unique(lab[b])] = 1
+        any_a[0] = any_b[0] = 0
+        return tmin, tmax, any_a, any_b
 
 
 def _label_case():
@@ -133,6 +162,55 @@ def test_sharded_label_equals_unsharded(world, overlap, absolute):
         assert p.exitcode == 0
     for rank, t0, t1, lab in got:
         assert np.array_equal(lab, want[t0:t1]), rank
+
+
+def _growth_case():
+    import make_golden as mg
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "growth_multi.npz"))
+    wvd = mg.growth_multi_case()[:, 10:110, 10:150].copy()
+    fwd = (g["fwd_q256"].astype(np.float32) / 256)[:, 10:110, 10:150].copy()
+    bwd = (g["bwd_q256"].astype(np.float32) / 256)[:, 10:110, 10:150].copy()
+    dt = np.full(wvd.shape[0], 5.0)
+    dt[5] = 5.5
+    return wvd, fwd, bwd, dt
+
+
+def _growth_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        wvd, fwd, bwd, dt = _growth_case()
+        t0, t1 = D.shard_bounds(wvd.shape[0], world, rank)
+        fl = D.ShardedFlow(torch.from_numpy(fwd[t0:t1].copy()), torch.from_numpy(bwd[t0:t1].copy()), rank, world,
+                           ops=OracleOps())
+        shard = D.make_shard(torch.from_numpy(wvd[t0:t1].copy()), rank, world)
+        smoothed, markers = fl.detect_growth_markers(shard, dt[t0:t1], t0)
+        q.put((rank, t0, t1, smoothed.numpy().copy(), markers.numpy().copy()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_growth_markers_equal_unsharded(world):
+    from oracle import detection_ops as det
+    wvd, fwd, bwd, dt = _growth_case()
+    want = det.detect_growth_markers(wvd, dt, fwd, bwd, intermediates=True)
+    assert want["markers"].max() >= 2 and want["linked"].max() > want["markers"].max()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_growth_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, t0, t1, smoothed, markers in got:
+        assert np.array_equal(smoothed, want["smoothed"][t0:t1], equal_nan=True), rank
+        assert np.array_equal(markers, want["markers"][t0:t1]), rank
 
 
 def _data():

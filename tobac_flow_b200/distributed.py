@@ -62,6 +62,52 @@ class CudaOps:
         from .label import relabel_device
         return relabel_device(flat, mapping)
 
+    # -- growth-marker detection (the per-frame filters of detection.py:98-118 are local to a rank) -------------------
+    def scale_frames(self, raw32, dt_minutes):
+        from . import _lib
+        from .flow import _stream
+        T, H, W = raw32.shape
+        dt = torch.from_numpy(np.ascontiguousarray(np.asarray(dt_minutes, np.float64))).to(raw32.device)
+        out = torch.empty((T, H, W), dtype=torch.float64, device=raw32.device)
+        _lib.check(_lib.load().tf_scale_frames(raw32.data_ptr(), dt.data_ptr(), out.data_ptr(), T, H, W, _stream()),
+                   "tf_scale_frames")
+        return out
+
+    def growth_seed_masks(self, smoothed, wvd):
+        """(filtered >= 0.5, wvd >= -5, opened(filtered >= 0.25)) as uint8 tensors: detection.py:105-119."""
+        from . import _lib
+        from .detection import curvature_filter_device, grey_opening_cross_device, _float_code
+        from .flow import _stream
+        lib = _lib.load()
+        T, H, W = smoothed.shape
+        n = smoothed.numel()
+        opened = grey_opening_cross_device(smoothed)
+        curv = curvature_filter_device(wvd)
+        filtered = torch.empty_like(opened)
+        _lib.check(lib.tf_mask_multiply(opened.data_ptr(), curv.data_ptr(), filtered.data_ptr(), _float_code(opened), n,
+                                        _stream()), "tf_mask_multiply")
+        m025, m05, warm, seeds = (torch.empty((T, H, W), dtype=torch.uint8, device=smoothed.device) for _ in range(4))
+        for src, thr, dst in ((filtered, 0.25, m025), (filtered, 0.5, m05), (wvd, -5.0, warm)):
+            _lib.check(lib.tf_threshold_ge(src.data_ptr(), thr, dst.data_ptr(), _float_code(src), n, _stream()),
+                       "tf_threshold_ge")
+        _lib.check(lib.tf_binary_opening_cross(m025.data_ptr(), seeds.data_ptr(), T, H, W, _stream()),
+                   "tf_binary_opening_cross")
+        return m05, warm, seeds
+
+    def label_stats(self, labels, mask_a, mask_b, n_labels):
+        """(tmin, tmax, any_a, any_b) host arrays of n_labels + 1 entries over this rank's frames (local frame indices;
+        tmax = -1 and tmin huge where the label does not occur here)."""
+        from . import _lib
+        from .flow import _stream
+        T = labels.shape[0]
+        hw = labels.numel() // max(T, 1)
+        st = torch.empty((4, n_labels + 1), dtype=torch.int32, device=labels.device)
+        _lib.check(_lib.load().tf_label_stats(labels.data_ptr(), mask_a.data_ptr(), mask_b.data_ptr(), T, hw, n_labels,
+                                              st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr(),
+                                              _stream()), "tf_label_stats")
+        h = st.cpu().numpy()
+        return h[0], h[1], h[2], h[3]
+
 
 def _p2p(ops, group):
     if ops:
@@ -132,7 +178,7 @@ class ShardedFlow:
         return self.ops.convolve(shard.stencil_view(), self.fwd, self.bwd, structure, method, fill_value, dtype,
                                  reducer, shard.has_prev, shard.has_next, out)
 
-    def label(self, mask_local, structure=None, overlap: float = 0.0, absolute_overlap: int = 1):
+    def label(self, mask_local, structure=None, overlap: float = 0.0, absolute_overlap: int = 1, return_count=False):
         """``Flow.label`` (tobac_flow/flow.py:281-330 -> label.py:84-175) on a time-sharded mask: every rank passes the
         (T_loc, H, W) mask of its own frames and gets the labels of those frames, numbered exactly as the unsharded
         call numbers them.
@@ -180,8 +226,40 @@ class ShardedFlow:
             dist.all_gather(tables, table, group=self.group)
             keys = np.concatenate([t[0, :n].cpu().numpy().view(np.uint64) for t, n in zip(tables, lens)])
             cnts = np.concatenate([t[1, :n].cpu().numpy().astype(np.int32) for t, n in zip(tables, lens)])
-        mapping, _ = link_groups_host(keys, cnts, sizes, total, overlap, absolute_overlap)
-        return self.ops.relabel(shard.local.contiguous(), mapping)
+        mapping, n_obj = link_groups_host(keys, cnts, sizes, total, overlap, absolute_overlap)
+        out = self.ops.relabel(shard.local.contiguous(), mapping)
+        return (out, n_obj) if return_count else out
+
+    def detect_growth_markers(self, wvd: "Shard", dt_minutes_local, t0: int = 0):
+        """``detect_growth_markers`` (tobac_flow/detection.py:98-125) on a time-sharded field: returns
+        (wvd_diff_smoothed, marker_labels) for this rank's frames, identical to the unsharded call.
+
+        ``wvd`` is this rank's Shard of the float32 field, ``dt_minutes_local`` the centred time differences of its
+        frames (get_time_diff_from_coord evaluated on the whole series, sliced), ``t0`` its first global frame index.
+        Exchanges: one-frame halos of the field and of the raw derivative (point to point), the labelling exchange of
+        ``label``, and a min / max reduction of the per-label time extent and mask hits (one int per label)."""
+        ops = self.ops
+        s_t = np.zeros((3, 3, 3))
+        s_t[:, 1, 1] = 1
+        raw32 = self.convolve(wvd, s_t, reducer=1)                                     # Flow.diff       (:99)
+        raw = make_shard(ops.scale_frames(raw32, dt_minutes_local), self.rank, self.world)   # / dt      (:100)
+        smoothed = self.convolve(raw, s_t, reducer=2)                                  # filtered_tdiff  (:103)
+        m05, warm, seeds = ops.growth_seed_masks(smoothed, wvd.local.contiguous())     # :105-112
+        linked, n_obj = self.label(seeds, overlap=0.0, absolute_overlap=1, return_count=True)
+        tmin, tmax, any_a, any_b = ops.label_stats(linked, m05, warm, n_obj)
+        dev = linked.device
+        present = tmax >= 0
+        lo = torch.from_numpy(np.where(present, tmin.astype(np.int64) + t0, np.iinfo(np.int32).max)).to(dev)
+        hi = torch.from_numpy(np.stack([np.where(present, tmax.astype(np.int64) + t0, -1), any_a.astype(np.int64),
+                                        any_b.astype(np.int64)])).to(dev)
+        if self.world > 1:
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+        lo, hi = lo.cpu().numpy(), hi.cpu().numpy()
+        wh = ((hi[0, 1:] - lo[1:] + 1) >= 3) & (hi[1, 1:] != 0) & (hi[2, 1:] != 0)     # :114-119
+        remap = np.zeros(n_obj + 1, np.int32)
+        remap[1:] = np.cumsum(wh) * wh
+        return smoothed, ops.relabel(linked, remap)
 
 
 def create_flow_sharded(shard: Shard, smoothing_passes=0, interp_method="linear", max_value=20, ops=None, group=None,
