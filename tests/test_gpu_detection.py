@@ -300,3 +300,18 @@ def test_sharded_label_single_rank_cuda_backend(multi):
     assert np.array_equal(lab.cpu().numpy(), g["linked"])
     lab = fl.label(torch.from_numpy(seeds).cuda(), overlap=0.5, absolute_overlap=4)
     assert np.array_equal(lab.cpu().numpy(), g["linked_ov"])
+
+
+def test_sharded_growth_markers_single_rank_cuda_backend(multi):
+    """ShardedFlow.detect_growth_markers with the CUDA back-end on one rank equals the single-call pipeline and the
+    reference golden (collectives are skipped at world size 1; gloo tests and scratch/detect_sharded_check.py cover them)."""
+    from tobac_flow_b200 import distributed as D
+    from tobac_flow_b200.detection import growth_markers_device
+    g, wvd, fwd, bwd, flow = multi
+    dt = np.full(wvd.shape[0], 5.0)
+    fl = D.ShardedFlow(torch.from_numpy(fwd).cuda(), torch.from_numpy(bwd).cuda(), 0, 1)
+    shard = D.make_shard(torch.from_numpy(wvd).cuda(), 0, 1)
+    smoothed, markers = fl.detect_growth_markers(shard, dt, 0)
+    ref = growth_markers_device(flow, torch.from_numpy(wvd).cuda(), dt)
+    assert torch.equal(torch.nan_to_num(smoothed, nan=-7.0), torch.nan_to_num(ref["smoothed"], nan=-7.0))
+    assert np.array_equal(markers.cpu().numpy(), g["markers"])
