@@ -315,3 +315,16 @@ def test_sharded_growth_markers_single_rank_cuda_backend(multi):
     ref = growth_markers_device(flow, torch.from_numpy(wvd).cuda(), dt)
     assert torch.equal(torch.nan_to_num(smoothed, nan=-7.0), torch.nan_to_num(ref["smoothed"], nan=-7.0))
     assert np.array_equal(markers.cpu().numpy(), g["markers"])
+
+
+def test_growth_markers_float64_field(multi):
+    """A float64 field is smoothed / thresholded in float64 (scipy keeps the array dtype): same result as the oracle."""
+    from tobac_flow_b200.detection import growth_markers_device
+    g, wvd, fwd, bwd, flow = multi
+    w64 = wvd.astype(np.float64) + 1e-9 * np.arange(wvd.shape[2])[None, None, :]
+    dt = np.full(wvd.shape[0], 5.0)
+    r = growth_markers_device(flow, torch.from_numpy(w64).cuda(), dt)
+    want = det.detect_growth_markers(w64, dt, fwd, bwd, backend=BACKEND, intermediates=True)
+    assert np.array_equal(r["smoothed"].cpu().numpy(), want["smoothed"], equal_nan=True)
+    assert np.array_equal(r["seeds"].cpu().numpy().astype(bool), want["seeds"])
+    assert np.array_equal(r["markers"].cpu().numpy(), want["markers"])

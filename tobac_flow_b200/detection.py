@@ -117,7 +117,7 @@ def time_diff_minutes(t_coord) -> np.ndarray:
 
 def growth_markers_device(flow: Flow, wvd: torch.Tensor, dt_minutes) -> dict:
     """The whole of detection.py:98-118 on device tensors; returns the intermediates the reference exposes plus the
-    markers.  ``wvd`` (T, H, W) float32 CUDA tensor, ``dt_minutes`` T doubles."""
+    markers.  ``wvd`` (T, H, W) float32 or float64 CUDA tensor, ``dt_minutes`` T doubles."""
     lib = _lib.load()
     dev = wvd.device
     T, H, W = wvd.shape
@@ -230,7 +230,9 @@ def detect_growth_markers(flow, wvd):
         raise AttributeError("wvd needs a time coordinate `.t` (detection.py:100)")
     dt = time_diff_minutes(t_coord)
     on_device = isinstance(wvd, torch.Tensor) and wvd.is_cuda
-    w, _ = _to_device(wvd if isinstance(wvd, torch.Tensor) else _as_numpy(wvd), torch.float32)
+    w, _ = _to_device(wvd if isinstance(wvd, torch.Tensor) else _as_numpy(wvd))
+    if w.dtype not in (torch.float32, torch.float64):     # a float64 field is filtered in float64, as scipy would
+        w = w.to(torch.float32)
     r = growth_markers_device(flow, w, dt)
     if on_device:
         return r["smoothed"], r["markers"]
