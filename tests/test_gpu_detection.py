@@ -254,6 +254,10 @@ def test_get_growth_rate(multi, method):
     got = get_growth_rate(flow, da, method=method)
     want = det.get_growth_rate(wvd, np.full(wvd.shape[0], 5.0), fwd, bwd, method=method, backend=BACKEND)
     assert got.dtype == np.float32 and np.array_equal(got, want, equal_nan=True)
+    w64 = -wvd.astype(np.float64) * 1.000000123                       # a float64 field (detect_cores passes -bt)
+    got = get_growth_rate(flow, refshim.DataArray(w64, coords={"t": t}, dims=("t", "y", "x"), t=t), method=method)
+    want = det.get_growth_rate(w64, np.full(wvd.shape[0], 5.0), fwd, bwd, method=method, backend=BACKEND)
+    assert got.dtype == np.float32 and np.array_equal(got, want, equal_nan=True)
 
 
 def test_get_anvil_markers(multi):

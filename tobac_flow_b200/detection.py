@@ -164,7 +164,8 @@ def _time_coord(field):
 
 
 def growth_rate_device(flow: Flow, field: torch.Tensor, dt_minutes, method: str = "linear") -> torch.Tensor:
-    """``get_growth_rate`` on a float32 CUDA tensor: Flow.diff / dt, then the 5-point same-step nanmean (float32)."""
+    """``get_growth_rate`` on a float32 / float64 CUDA tensor: Flow.diff / dt, then the 5-point same-step nanmean
+    (float32 result)."""
     T, H, W = field.shape
     raw32 = flow.diff(field, method=method)
     dt = torch.from_numpy(np.ascontiguousarray(np.asarray(dt_minutes, np.float64))).to(field.device)
@@ -182,7 +183,9 @@ def get_growth_rate(flow, field, method: str = "linear"):
     """detection.py:168-198: growth / cooling rate of ``field`` (an array with a ``.t`` time coordinate)."""
     dt = _time_coord(field)
     on_device = isinstance(field, torch.Tensor) and field.is_cuda
-    f, _ = _to_device(field if isinstance(field, torch.Tensor) else _as_numpy(field), torch.float32)
+    f, _ = _to_device(field if isinstance(field, torch.Tensor) else _as_numpy(field))
+    if f.dtype not in (torch.float32, torch.float64):     # the taps are warped in the field's own dtype (cv2.remap)
+        f = f.to(torch.float32)
     r = growth_rate_device(flow, f, dt, method)
     return r if on_device else _to_host(r)
 
