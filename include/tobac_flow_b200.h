@@ -92,6 +92,12 @@ size_t tf_farneback_workspace_bytes(int n_pairs, int H, int W, const tf_fb_param
 int tf_pair_normalise_u8(const float* f0, const float* f1, long long frame_stride, uint8_t* q0, uint8_t* q1,
                          int n_pairs, int H, int W, float* minmax_scratch, void* stream);
 
+/* The same for float64 frames: numpy keeps the array dtype, so the reference then normalises in float64
+ * (normalisation_utils.py:59-72, 10-33), which is not bit-identical to casting the frames to float32 first.
+ * minmax_scratch: 2 * n_pairs doubles. */
+int tf_pair_normalise_u8_f64(const double* f0, const double* f1, long long frame_stride, uint8_t* q0, uint8_t* q1,
+                             int n_pairs, int H, int W, double* minmax_scratch, void* stream);
+
 /*
  * Forward and backward Farneback flow for n_pairs quantised pairs.
  * Replaces of_model.calc(prev, next, None) and of_model.calc(next, prev, None)

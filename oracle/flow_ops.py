@@ -41,13 +41,16 @@ def have_cv2() -> bool:
 # normalisation (normalisation_utils.py:59-72 then :10-33 with vmin=0, vmax=1)
 # ----------------------------------------------------------------------------------------------
 def pair_to_u8(frame0: np.ndarray, frame1: np.ndarray):
-    pair = np.stack([frame0, frame1]).astype(F32, copy=False)
+    pair = np.stack([frame0, frame1])
+    if pair.dtype != F32:
+        pair = pair.astype(np.float64, copy=False)   # numpy keeps float64 and promotes integers: the reference then
+    one = pair.dtype.type(1)                         # normalises in float64
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         lo = np.nanmin(pair)
         hi = np.nanmax(pair)
     with np.errstate(invalid="ignore", over="ignore", divide="ignore"):
-        factor = F32(1) / (hi - lo) if hi > lo else F32(0)
+        factor = one / (hi - lo) if hi > lo else pair.dtype.type(0)
         scaled = (pair - lo) * factor
         scaled = np.maximum(np.minimum(scaled, 1), 0)  # NaN propagates
         scaled = (scaled - 0) * 255.0  # python float keeps the fp32 array dtype

@@ -410,3 +410,28 @@ def test_sobel_around_nan_inf_and_wild_flow():
     assert np.array_equal(np.isinf(got), np.isinf(want))
     ok = np.isfinite(want)
     assert np.max(np.abs(got[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1.0)) < 1e-12
+
+
+def test_float64_frames_are_normalised_in_float64():
+    """float64 (and integer) frames: numpy keeps / promotes the dtype, so the reference quantises them in float64; the
+    u8 pair must match that bit for bit (casting to float32 first moves a few per cent of the pixels by one count)."""
+    import tobac_flow_b200 as tfb
+    bt = synthetic.bt_sequence(3, 120, 160, seed=3, nans=True).astype(np.float64) * 1.0000001
+    bt[1, 5:8] = np.nan
+    moved = 0
+    for i in range(2):
+        q0, q1 = tfb.pair_to_8bit(bt[i], bt[i + 1])
+        r0, r1 = ops.pair_to_u8(bt[i], bt[i + 1])
+        assert np.array_equal(q0, r0) and np.array_equal(q1, r1)
+        s0, s1 = ops.pair_to_u8(bt[i].astype(np.float32), bt[i + 1].astype(np.float32))
+        moved += int((r0 != s0).sum() + (r1 != s1).sum())
+    assert moved > 0                                   # the case does distinguish the two arithmetic paths
+    bi = np.nan_to_num(bt * 10).astype(np.int32)
+    q0, q1 = tfb.pair_to_8bit(bi[0], bi[1])
+    r0, r1 = ops.pair_to_u8(bi[0], bi[1])
+    assert np.array_equal(q0, r0) and np.array_equal(q1, r1)
+    f = tfb.create_flow(bt)
+    rf, rb = ops.create_flow(bt, backend="cv2" if ops.have_cv2() else "numpy")
+    for mine, ref in ((f.forward_flow, rf), (f.backward_flow, rb)):
+        e = np.sqrt(((mine - ref) ** 2).sum(-1))
+        assert e.mean() <= 1e-3 and np.percentile(e, 99) <= 1e-2, (e.mean(), e.max())

@@ -20,7 +20,7 @@ TF_NEAREST, TF_LINEAR, TF_CUBIC = 0, 1, 2
 # every symbol include/tobac_flow_b200.h declares
 EXPORTS = (
     "tf_version", "tf_last_error", "tf_fb_default_params", "tf_fb_level_plan", "tf_fb_poly_constants",
-    "tf_farneback_workspace_bytes", "tf_pair_normalise_u8", "tf_farneback_pairs", "tf_smooth_flow_step",
+    "tf_farneback_workspace_bytes", "tf_pair_normalise_u8", "tf_pair_normalise_u8_f64", "tf_farneback_pairs", "tf_smooth_flow_step",
     "tf_flow_finalise", "tf_sl_convolve", "tf_profile_enable", "tf_profile_reset", "tf_profile_read",
     "tf_vr_default_params", "tf_vr_workspace_bytes", "tf_variational_refinement",
     "tf_ccl_workspace_bytes", "tf_flat_label", "tf_binary_fill_holes", "tf_gaussian_filter_yx", "tf_curvature_mask",
@@ -76,6 +76,8 @@ def load():
     lib.tf_farneback_workspace_bytes.argtypes = [ci, ci, ci, pp]
     lib.tf_farneback_workspace_bytes.restype = ctypes.c_size_t
     lib.tf_pair_normalise_u8.argtypes = [vp, vp, ll, vp, vp, ci, ci, ci, vp, vp]
+    lib.tf_pair_normalise_u8_f64.argtypes = lib.tf_pair_normalise_u8.argtypes
+    lib.tf_pair_normalise_u8_f64.restype = ci
     lib.tf_farneback_pairs.argtypes = [vp, vp, vp, ll, vp, ll, ci, ci, ci, pp, vp, ctypes.c_size_t, vp]
     lib.tf_smooth_flow_step.argtypes = [vp, vp, vp, vp, ll, ci, ci, ci, ci, vp]
     lib.tf_flow_finalise.argtypes = [vp, vp, ci, ci, ci, cf, ci, ci, ci, vp]

@@ -129,6 +129,72 @@ __global__ void __launch_bounds__(256) pair_quantise_kernel(const float* __restr
     }
 }
 
+// ---- float64 frames: the reference then normalises in float64 (numpy keeps the array dtype), which moves a few
+// pixels across a truncation boundary relative to the float32 arithmetic above ----------------------------------------
+__device__ __forceinline__ long long d2key(double d) {
+    long long i = __double_as_longlong(d);
+    return i >= 0 ? i : i ^ 0x7fffffffffffffffLL;
+}
+__device__ __forceinline__ double key2d(long long k) { return __longlong_as_double(k >= 0 ? k : k ^ 0x7fffffffffffffffLL); }
+
+__global__ void minmax_init_f64_kernel(long long* mm, int n_pairs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pairs) {
+        mm[2 * i] = d2key((double)INFINITY);
+        mm[2 * i + 1] = d2key(-(double)INFINITY);
+    }
+}
+
+__global__ void __launch_bounds__(256) pair_minmax_f64_kernel(const double* __restrict__ f0, const double* __restrict__ f1,
+                                                              long long frame_stride, int n, long long* __restrict__ mm) {
+    const int p = blockIdx.y;
+    const double* a = f0 + (long long)p * frame_stride;
+    const double* b = f1 + (long long)p * frame_stride;
+    double lo = INFINITY, hi = -INFINITY;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double u = a[i], v = b[i];
+        lo = fmin(fmin(lo, u), v);      // fmin / fmax ignore NaN operands == nanmin / nanmax
+        hi = fmax(fmax(hi, u), v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm + 2 * p, d2key(lo));
+        atomicMax(mm + 2 * p + 1, d2key(hi));
+    }
+}
+
+__global__ void __launch_bounds__(256) pair_quantise_f64_kernel(const double* __restrict__ f0, const double* __restrict__ f1,
+                                                                long long frame_stride, int n,
+                                                                const long long* __restrict__ mm, uint8_t* __restrict__ q0,
+                                                                uint8_t* __restrict__ q1) {
+    const int p = blockIdx.y;
+    const double* a = f0 + (long long)p * frame_stride;
+    const double* b = f1 + (long long)p * frame_stride;
+    uint8_t* oa = q0 + (long long)p * n;
+    uint8_t* ob = q1 + (long long)p * n;
+    const double lo = key2d(mm[2 * p]), hi = key2d(mm[2 * p + 1]);
+    const double factor = (hi > lo) ? __ddiv_rn(1.0, __dsub_rn(hi, lo)) : 0.0;
+    auto norm255 = [&](double x) {
+        double v = __dmul_rn(__dsub_rn(x, lo), factor);
+        if (v == v) v = fmax(fmin(v, 1.0), 0.0);
+        return __dmul_rn(v, 255.0);
+    };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double a0 = norm255(a[i]), a1 = norm255(b[i]);
+        const bool k0 = isfinite(a0), k1 = isfinite(a1);
+        if (!k0) a0 = 127.0;
+        if (!k1) a1 = 127.0;
+        if (!k0) a0 = a1;
+        if (!k1) a1 = a0;
+        oa[i] = (uint8_t)a0;
+        ob[i] = (uint8_t)a1;
+    }
+}
+
 }  // namespace tf
 
 extern "C" int tf_pair_normalise_u8(const float* f0, const float* f1, long long frame_stride, uint8_t* q0, uint8_t* q1,
@@ -160,4 +226,32 @@ extern "C" int tf_pair_normalise_u8(const float* f0, const float* f1, long long 
                                                   q1 + (long long)p0 * n);
     }
     return check_launch("tf_pair_normalise_u8");
+}
+
+extern "C" int tf_pair_normalise_u8_f64(const double* f0, const double* f1, long long frame_stride, uint8_t* q0, uint8_t* q1,
+                                        int n_pairs, int H, int W, double* minmax_scratch, void* stream) {
+    using namespace tf;
+    if (n_pairs == 0) return TF_OK;
+    if (!f0 || !f1 || !q0 || !q1 || !minmax_scratch || n_pairs < 0 || H <= 0 || W <= 0) {
+        set_error("tf_pair_normalise_u8_f64: invalid argument");
+        return TF_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long n64 = (long long)H * W;
+    if (n64 > 0x7fffffffLL) { set_error("tf_pair_normalise_u8_f64: frame too large"); return TF_ERR_INVALID_ARGUMENT; }
+    const int n = (int)n64;
+    long long* mm = reinterpret_cast<long long*>(minmax_scratch);
+    LaunchTimer lt(KC_NORMALISE, 34.0 * n * n_pairs, s, 1 + 2 * cdiv(n_pairs, 65535));
+    minmax_init_f64_kernel<<<cdiv(n_pairs, 128), 128, 0, s>>>(mm, n_pairs);
+    const int bx = min(max(cdiv(n, 256 * 8), 1), 1184);
+    for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
+        const int np = min(n_pairs - p0, 65535);
+        dim3 grid(bx, np);
+        pair_minmax_f64_kernel<<<grid, 256, 0, s>>>(f0 + (long long)p0 * frame_stride, f1 + (long long)p0 * frame_stride,
+                                                    frame_stride, n, mm + 2 * p0);
+        pair_quantise_f64_kernel<<<grid, 256, 0, s>>>(f0 + (long long)p0 * frame_stride, f1 + (long long)p0 * frame_stride,
+                                                      frame_stride, n, mm + 2 * p0, q0 + (long long)p0 * n,
+                                                      q1 + (long long)p0 * n);
+    }
+    return check_launch("tf_pair_normalise_u8_f64");
 }

@@ -506,7 +506,7 @@ def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Te
                           frames_ready: Callable | None = None) -> None:
     """Fill ``fwd[i]`` and ``bwd[i + 1]`` for every consecutive pair of ``frames`` (device tensors, in place).
 
-    ``frames`` (T, H, W) float32; ``fwd``/``bwd`` (>= T, H, W, 2) float32.  With ``next_frames`` the pairs are
+    ``frames`` (T, H, W) float32 or float64; ``fwd``/``bwd`` (>= T, H, W, 2) float32.  With ``next_frames`` the pairs are
     (frames[i], next_frames[i]) and results go to fwd[i], bwd[i + 1] for every i (``calculate_flow_2``).
     ``max_value`` fuses the clamp of ``create_flow`` into the last kernel when no smoothing follows.
     """
@@ -523,7 +523,9 @@ def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Te
     dev = frames.device
     q0 = torch.empty((nb, H, W), dtype=torch.uint8, device=dev)
     q1 = torch.empty((nb, H, W), dtype=torch.uint8, device=dev)
-    mm = torch.empty((2 * nb,), dtype=torch.float32, device=dev)
+    f64 = frames.dtype == torch.float64        # float64 frames are normalised in float64, as numpy does for the reference
+    mm = torch.empty((2 * nb,), dtype=frames.dtype, device=dev)
+    normalise = lib.tf_pair_normalise_u8_f64 if f64 else lib.tf_pair_normalise_u8
     ws_bytes = _lib.workspace_bytes(nb, H, W, params)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     vr_params = vr_ws = None
@@ -545,7 +547,7 @@ def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Te
             frames_ready(p0 + n)          # make the stream wait until frames [0, p0 + n] have been uploaded
         f0 = frames.data_ptr() + p0 * hw * es
         f1 = (frames.data_ptr() + (p0 + 1) * hw * es) if next_frames is None else (next_frames.data_ptr() + p0 * hw * es)
-        _lib.check(lib.tf_pair_normalise_u8(f0, f1, hw, q0.data_ptr(), q1.data_ptr(), n, H, W, mm.data_ptr(), st),
+        _lib.check(normalise(f0, f1, hw, q0.data_ptr(), q1.data_ptr(), n, H, W, mm.data_ptr(), st),
                    "tf_pair_normalise_u8")
         fo = fwd.data_ptr() + p0 * hw * 2 * 4
         bo = bwd.data_ptr() + (p0 + 1) * hw * 2 * 4
@@ -602,12 +604,14 @@ def _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_meth
             torch.cuda.current_stream().wait_event(events[min(last_frame // _HOST_PAIR_BATCH, len(events) - 1)])
         batch = _HOST_PAIR_BATCH
     else:
-        frames, _ = _to_device(data, torch.float32)
+        frames, _ = _to_device(data)
+        if frames.dtype not in (torch.float32, torch.float64):
+            frames = frames.to(torch.float64)      # integer data: numpy promotes (array - vmin) * factor to float64
     if frames.dim() != 3:
         raise ValueError("data must have shape (t, y, x)")
     frames_b = None
     if data_b is not None:
-        frames_b, _ = _to_device(data_b, torch.float32)
+        frames_b, _ = _to_device(data_b, frames.dtype)
     T, H, W = frames.shape
     # the reference pre-fills with NaN (flow.py:408-409); for T > 1 every element is overwritten (pairs + end
     # rules), so the fill is only materialised for the degenerate single-frame case
@@ -672,13 +676,16 @@ def smooth_flow_step(forward_flow, backward_flow, method: str = "linear"):
 
 
 def pair_to_8bit(frame0, frame1):
-    """``to_8bit(linear_norm(stack), 0, 1)`` for one pair (normalisation_utils.py:59-72, 10-33)."""
+    """``to_8bit(linear_norm(stack), 0, 1)`` for one pair (normalisation_utils.py:59-72, 10-33); float64 frames are
+    normalised in float64, as numpy does."""
     a, host = _to_device(np.stack([_as_numpy(frame0), _as_numpy(frame1)]) if not isinstance(frame0, torch.Tensor)
-                         else torch.stack([frame0, frame1]), torch.float32)
+                         else torch.stack([frame0, frame1]))
+    if a.dtype not in (torch.float32, torch.float64):
+        a = a.to(torch.float64)
     _, H, W = a.shape
     q = torch.empty((2, H, W), dtype=torch.uint8, device=a.device)
-    mm = torch.empty((2,), dtype=torch.float32, device=a.device)
-    _lib.check(_lib.load().tf_pair_normalise_u8(a.data_ptr(), a.data_ptr() + H * W * 4, H * W, q.data_ptr(),
-                                                q.data_ptr() + H * W, 1, H, W, mm.data_ptr(), _stream()),
-               "tf_pair_normalise_u8")
+    mm = torch.empty((2,), dtype=a.dtype, device=a.device)
+    fn = _lib.load().tf_pair_normalise_u8_f64 if a.dtype == torch.float64 else _lib.load().tf_pair_normalise_u8
+    _lib.check(fn(a.data_ptr(), a.data_ptr() + H * W * a.element_size(), H * W, q.data_ptr(), q.data_ptr() + H * W, 1, H,
+                  W, mm.data_ptr(), _stream()), "tf_pair_normalise_u8")
     return (q[0].cpu().numpy(), q[1].cpu().numpy()) if host else (q[0], q[1])
