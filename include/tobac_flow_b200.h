@@ -78,6 +78,22 @@ int tf_fb_level_plan(int H, int W, const tf_fb_params* p /* host */, int* hs /* 
  * ig55.  `out` is a host array of 22 floats. */
 int tf_fb_poly_constants(const tf_fb_params* p /* host */, float* out /* host */);
 
+/* Stage-level entry points of the Farneback pipeline (parity tests against the oracle's per-stage restatement of
+ * OpenCV's optflowgf.cpp; tf_farneback_pairs runs exactly these launches).
+ *
+ * tf_fb_pyramid_level: level image `level` (index into tf_fb_level_plan, coarsest first) of the quantised pair
+ *   (q0, q1: (n_pairs, H, W) u8) = convertTo(CV_32F) -> GaussianBlur(ksize, sigma) -> resize(INTER_LINEAR), always
+ *   from the full-resolution image.  out: (2 * n_pairs, h, w) fp32, image 2p = q0[p], 2p + 1 = q1[p].
+ *   `workspace` as for tf_farneback_pairs.  flags bit 0: use the separable two-pass path through scratch instead of
+ *   the fused tile kernels (both give the same bits).
+ * tf_fb_polyexp: FarnebackPolyExp of `n_img` fp32 images I (n_img, h, w) -> R: per image `tf_fb_r_stride(h, w)`
+ *   floats = a float4 plane (c0..c3 per pixel: OpenCV's r[0..3] order is c0 = d/dy, c1 = d/dx, c2 = yy, c3 = xx)
+ *   followed by a float plane (c4 = xy). */
+int tf_fb_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int H, int W, const tf_fb_params* p /* host */,
+                        int level, float* out, void* workspace, size_t workspace_bytes, int flags, void* stream);
+long long tf_fb_r_stride(int h, int w);
+int tf_fb_polyexp(const float* I, int n_img, int h, int w, const tf_fb_params* p /* host */, float* R, void* stream);
+
 /* Bytes of scratch tf_farneback_pairs needs for `n_pairs` pairs of H x W frames. */
 size_t tf_farneback_workspace_bytes(int n_pairs, int H, int W, const tf_fb_params* p /* host */);
 

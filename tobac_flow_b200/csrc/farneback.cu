@@ -77,7 +77,9 @@ static Workspace carve(void* base, int n_pairs, int H, int W, const LevelPlan& l
     ws.flow[0] = reinterpret_cast<float*>(b + o_f0);
     ws.flow[1] = reinterpret_cast<float*>(b + o_f1);
     ws.flow[2] = reinterpret_cast<float*>(b + o_f2);
-    ws.total = off;
+    // tail pad: the staged (bulk-copy) rows of the iteration kernel are rounded up to 16-byte granules and may read a
+    // few bytes past the last flow row
+    ws.total = off + 256;
     return ws;
 }
 
@@ -133,6 +135,37 @@ extern "C" size_t tf_farneback_workspace_bytes(int n_pairs, int H, int W, const 
     if (validate_params(p) != TF_OK || n_pairs <= 0 || H <= 0 || W <= 0) return 0;
     LevelPlan lp = make_level_plan(H, W, *p);
     return carve(nullptr, n_pairs, H, W, lp).total;
+}
+
+extern "C" int tf_fb_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int H, int W, const tf_fb_params* p,
+                                   int level, float* out, void* workspace, size_t workspace_bytes, int flags, void* stream) {
+    if (n_pairs == 0) return TF_OK;
+    int rc = validate_params(p);
+    if (rc != TF_OK) return rc;
+    if (!q0 || !q1 || !out || !workspace || n_pairs < 0 || H <= 0 || W <= 0) {
+        set_error("tf_fb_pyramid_level: invalid argument");
+        return TF_ERR_INVALID_ARGUMENT;
+    }
+    const LevelPlan lp = make_level_plan(H, W, *p);
+    if (level < 0 || level >= lp.n) { set_error("tf_fb_pyramid_level: level %d out of range (%d levels)", level, lp.n); return TF_ERR_INVALID_ARGUMENT; }
+    const Workspace ws = carve(workspace, n_pairs, H, W, lp);
+    if (ws.total > workspace_bytes) {
+        set_error("tf_fb_pyramid_level: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+        return TF_ERR_WORKSPACE_TOO_SMALL;
+    }
+    return launch_pyramid_level(q0, q1, n_pairs, H, W, lp.h[level], lp.w[level], lp.ksize[level], lp.sigma[level], ws.tmp, out,
+                                (cudaStream_t)stream, (flags & 1) != 0);
+}
+
+extern "C" long long tf_fb_r_stride(int h, int w) { return r_img_stride(h, w); }
+
+extern "C" int tf_fb_polyexp(const float* I, int n_img, int h, int w, const tf_fb_params* p, float* R, void* stream) {
+    if (n_img == 0) return TF_OK;
+    int rc = validate_params(p);
+    if (rc != TF_OK) return rc;
+    if (!I || !R || n_img < 0 || h <= 0 || w <= 0) { set_error("tf_fb_polyexp: invalid argument"); return TF_ERR_INVALID_ARGUMENT; }
+    const PolyConsts pc = make_poly_consts(p->poly_n, p->poly_sigma);
+    return launch_polyexp(I, R, r_img_stride(h, w), n_img, h, w, pc, (cudaStream_t)stream);
 }
 
 extern "C" int tf_farneback_pairs(const uint8_t* q0, const uint8_t* q1, float* fwd, long long fwd_stride, float* bwd,

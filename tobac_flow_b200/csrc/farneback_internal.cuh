@@ -17,8 +17,9 @@ struct PolyConsts {
 PolyConsts make_poly_consts(int n, double sigma);
 
 // level image for 2*n_pairs images: out (2*n_pairs, h, w); tmp >= 2*n_pairs * rows*W floats
+// two_pass: the separable path through `tmp` instead of the fused tile kernels (same bits; kept for parity tests)
 int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int H, int W, int h, int w, int ksize,
-                         double sigma, float* tmp, float* out, cudaStream_t s);
+                         double sigma, float* tmp, float* out, cudaStream_t s, bool two_pass = false);
 
 // dst (n_fields, h, w, 2) = resize(src (n_fields, sh, sw, 2)) * mul; src == nullptr -> zeros
 int launch_flow_upsample(const float* src, float* dst, int n_fields, int sh, int sw, int h, int w, float mul,

@@ -40,7 +40,10 @@ constexpr int IT_HALO = 6, IT_WIN = 13, IT_RB = 4;
 #define TF_L2_PREFETCH_ROWS 0
 #endif
 constexpr int IT_PREFETCH_ROWS = TF_L2_PREFETCH_ROWS;
-#define TF_PF 1      // rows of taps in flight ahead of the row being computed
+#ifndef TF_DEEP
+#define TF_DEEP 0    // 1: a row's tap registers are re-loaded for the row after next as soon as they are blended
+#endif
+#define TF_PF (TF_DEEP ? 2 : 1)      // rows of taps in flight ahead of the row being computed
 #ifndef TF_FQ
 #define TF_FQ 4      // rows the flow loads run ahead of the tap issue that consumes them (4 or 2)
 #endif
@@ -67,12 +70,14 @@ __device__ __forceinline__ float ld_stream1(const float* p) {
 
 // HK = outputs per thread in the H phase = rows per H phase (4: after every M batch, vertical sums double-buffered;
 // 8: after every second M batch, single buffer, one more barrier).  Same shared-memory footprint either way.
-template <int NT, int HK, bool HS = false>
+template <int NT, int HK, bool HS = false, bool TM = false>
 struct StripCfg {
     static constexpr int OUT_W = NT - 2 * IT_HALO;
     static constexpr int VPAD = HS ? 0 : 8;                  // the shuffle H phase never reads beyond the strip
     static constexpr int VP = NT + 2 * VPAD;                 // pitch of a row of vertical sums (zero pads both sides)
-    static constexpr int RING_FLOATS = 3 * 3 * 5 * NT;       // 3 batches x prefix sums P0..P2 x 5 channels
+    // 3 batches x prefix sums P0..P2 x 5 channels; TM: the ring lives in tensor memory (thread-private columns)
+    static constexpr int RING_FLOATS = TM ? 0 : 3 * 3 * 5 * NT;
+    static constexpr int TM_COLS = 64;                       // 45 used; allocations are powers of two >= 32
     static constexpr int VBUF_ROWS = 8;                      // 2 x 4 (double-buffered) or 1 x 8
     static constexpr int VBUF_FLOATS = VBUF_ROWS * 5 * VP;
     static constexpr int SMEM_BYTES = (RING_FLOATS + VBUF_FLOATS) * (int)sizeof(float);
@@ -86,6 +91,23 @@ __device__ __forceinline__ float border_factor(int p, int n) {
     if (q < 5) s *= (q < 2 ? 0.14f : 0.4472f);
     return s;
 }
+
+// Tensor memory as thread-private scratch: with the 32x32b shape lane i of warp w addresses TMEM lane 32 * (w % 4) + i,
+// so a column is one private 32-bit word per thread.  The prefix-sum ring of the vertical window lives there: its
+// loads and stores then use the TMEM datapath (LDTM / STTM) instead of shared-memory wavefronts of the L1 data pipe,
+// which is the unit that limits this kernel.
+__device__ __forceinline__ void tm_ld5(float v[5], uint32_t a) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a) : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(v[4]) : "r"(a + 4) : "memory");
+}
+__device__ __forceinline__ void tm_st5(uint32_t a, const float v[5]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(a), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(a + 4), "f"(v[4]) : "memory");
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Everything one pixel's FarnebackUpdateMatrices reads: R0 at the pixel, the four bilinear taps of R1 at p + flow.
 struct Taps {
@@ -104,24 +126,37 @@ struct RPlanes {
 // issue the loads of one pixel (addresses are always valid; `inside` says whether the R1 taps are used)
 __device__ __forceinline__ void issue_taps(Taps& t, const RPlanes& R, int w, int h, int x, int y, float2 f) {
     const int o = y * w + x;
-    t.y = y;
     t.dx = f.x;
     t.dy = f.y;
     float fx = (float)x + f.x, fy = (float)y + f.y;
     const float flx = floorf(fx), fly = floorf(fy);
     const int x1 = (int)flx, y1 = (int)fly;
+#if !TF_DEEP
+    t.y = y;
     t.fx = fx - flx;
     t.fy = fy - fly;
     t.inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+#endif
     // out-of-image positions read a clamped (valid) 2x2 footprint whose values are then ignored; levels are never
     // narrower than 2 px in practice, and max(.., 0) keeps the address valid even then
+#ifndef TF_ABL
+#define TF_ABL 0     // timing ablations (wrong results): 1 = taps at the undisplaced pixel, 2 = no R1 loads
+#endif
+#if TF_ABL >= 1
+    const int xc = max(min(x, w - 2), 0), yc = max(min(y, h - 2), 0);
+#else
     const int xc = max(min(x1, w - 2), 0), yc = max(min(y1, h - 2), 0);
+#endif
     const float4* a0 = R.R1a + (yc * w + xc);
     const float4* a1 = a0 + w;
     const float* b0 = R.R1b + (yc * w + xc);
     const float* b1 = b0 + w;
     t.c = ld_stream(R.R0a + o);      // touched once by this CTA: do not displace the gather footprint in L1
     t.c4 = ld_stream1(R.R0b + o);
+#if TF_ABL == 2
+    t.p00 = t.p01 = t.p10 = t.p11 = t.c;
+    t.q00 = t.q01 = t.q10 = t.q11 = t.c4;
+#else
     t.p00 = __ldg(a0);
     t.p01 = __ldg(a0 + 1);
     t.p10 = __ldg(a1);
@@ -130,13 +165,25 @@ __device__ __forceinline__ void issue_taps(Taps& t, const RPlanes& R, int w, int
     t.q01 = __ldg(b0 + 1);
     t.q10 = __ldg(b1);
     t.q11 = __ldg(b1 + 1);
+#endif
 }
 
-// FarnebackUpdateMatrices for one pixel from its loaded taps
-__device__ __forceinline__ void matrix_from_taps(const Taps& t, int h, float sc_x, float m[5]) {
+// FarnebackUpdateMatrices for one pixel, part 1: everything that reads the loaded taps -> (r2..r6) before the border
+// scaling.  After this the tap registers are dead (TF_DEEP re-issues the loads of the row after next into them).
+// LEAN: the fractions / inside flag are recomputed from the flow (same arithmetic as issue_taps) instead of being kept
+// in registers next to the in-flight taps.
+template <bool LEAN = false>
+__device__ __forceinline__ void blend_taps(const Taps& t, float r[5], int w = 0, int h = 0, int x = 0, int y = 0) {
     float r2, r3, r4, r5, r6;
-    if (t.inside) {
-        const float fx = t.fx, fy = t.fy;
+    float fx = t.fx, fy = t.fy;
+    bool inside = t.inside;
+    if (LEAN) {
+        fx = (float)x + t.dx; fy = (float)y + t.dy;
+        const float flx = floorf(fx), fly = floorf(fy);
+        inside = (unsigned)(int)flx < (unsigned)(w - 1) && (unsigned)(int)fly < (unsigned)(h - 1);
+        fx -= flx; fy -= fly;
+    }
+    if (inside) {
         const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
         r2 = a00 * t.p00.x + a01 * t.p01.x + a10 * t.p10.x + a11 * t.p11.x;
         r3 = a00 * t.p00.y + a01 * t.p01.y + a10 * t.p10.y + a11 * t.p11.y;
@@ -156,8 +203,14 @@ __device__ __forceinline__ void matrix_from_taps(const Taps& t, int h, float sc_
     r3 = (t.c.y - r3) * 0.5f;
     r2 += r4 * t.dy + r6 * t.dx;
     r3 += r6 * t.dy + r5 * t.dx;
-    if (sc_x != 1.f || (unsigned)(t.y - 5) >= (unsigned)(h - 10)) {
-        const float sc = sc_x * border_factor(t.y, h);
+    r[0] = r2; r[1] = r3; r[2] = r4; r[3] = r5; r[4] = r6;
+}
+
+// part 2: border scaling and the five products
+__device__ __forceinline__ void matrix_from_blend(const float r[5], int y, int h, float sc_x, float m[5]) {
+    float r2 = r[0], r3 = r[1], r4 = r[2], r5 = r[3], r6 = r[4];
+    if (sc_x != 1.f || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+        const float sc = sc_x * border_factor(y, h);
         r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
     }
     m[0] = r4 * r4 + r6 * r6;
@@ -165,6 +218,12 @@ __device__ __forceinline__ void matrix_from_taps(const Taps& t, int h, float sc_
     m[2] = r5 * r5 + r6 * r6;
     m[3] = r4 * r2 + r6 * r3;
     m[4] = r6 * r2 + r5 * r3;
+}
+
+__device__ __forceinline__ void matrix_from_taps(const Taps& t, int h, float sc_x, float m[5]) {
+    float r[5];
+    blend_taps(t, r);
+    matrix_from_blend(r, t.y, h, sc_x, m);
 }
 
 // a*b - c*d with one rounding error in the result (Kahan)
@@ -177,17 +236,31 @@ __device__ __forceinline__ float diff_of_products(float a, float b, float c, flo
 
 // PS (persistent) selects the work distribution at compile time: the chunk-grid instantiation carries none of the
 // column loop's state (it needs the 128-register budget to itself; the persistent one spills 28 bytes).
-template <int NT, int HK, bool HS, bool PS>
+template <int NT, int HK, bool HS, bool PS, bool TM>
 __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : (HS ? TF_HS_CTAS : 4)))
 fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const float* __restrict__ flow_in,
                      float* __restrict__ out_fwd, long long fwd_stride, float* __restrict__ out_bwd,
                      long long bwd_stride, int h, int w, int chunk_rows, float clampv, int strips, int span_arg, int total) {
     const int span = PS ? span_arg : 0;
-    using C = StripCfg<NT, HK, HS>;
+    using C = StripCfg<NT, HK, HS, TM>;
     extern __shared__ __align__(16) float smem[];
     float* ring = smem;                       // [batch % 3][P0..P2][k][col]: prefix sums of the batch's rows
     float* vbuf = smem + C::RING_FLOATS;      // [buf][row][k][VP]
     const int tid = threadIdx.x;
+    uint32_t tm_base = 0;                     // TM: this warp's lane quarter, column 0 of the CTA's allocation
+    if constexpr (TM) {
+        static_assert(!TM || NT == 128, "tensor-memory ring: one TMEM lane per thread, 4 warps");
+        __shared__ uint32_t tm_addr_s;
+        if (tid < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(&tm_addr_s)), "n"(C::TM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tm_base = tm_addr_s + ((uint32_t)(tid >> 5) << 21);      // lane (bits 31:16) = 32 * warp
+    }
     const int dir = blockIdx.x & 1;
     const int plane = h * w;
     // Work distribution.  span == 0: one (strip, chunk, pair) per CTA from the grid.  span > 0 (persistent): the
@@ -235,8 +308,15 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
     const int hr = tid / (NT / HK), cg = tid % (NT / HK);
 
     // zero the suffix-sum ring column and the pads of the vertical-sum rows
+    if constexpr (TM) {
+        const float z[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int s = 0; s < 3 * 3 * 5; ++s) ring[s * NT + tid] = 0.f;
+        for (int s = 0; s < 9; ++s) tm_st5(tm_base + 5 * s, z);
+        tm_wait_st();
+    } else {
+#pragma unroll
+        for (int s = 0; s < 3 * 3 * 5; ++s) ring[s * NT + tid] = 0.f;
+    }
     if constexpr (C::VPAD > 0) {
         for (int i = tid; i < C::VBUF_ROWS * 5 * 2 * C::VPAD; i += NT) {
             const int rowk = i / (2 * C::VPAD), j = i % (2 * C::VPAD);
@@ -260,6 +340,10 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
     auto row_y = [&](int i) { return min(max(r_begin + i, 0), h - 1); };
     Taps cur;
     issue_taps(cur, RP, w, h, gx, row_y(0), ld_stream(fin + row_y(0) * w + gx));
+#if TF_DEEP
+    Taps cur1;                   // row i + 1 (the two sets alternate: S[i & 1] holds row i)
+    issue_taps(cur1, RP, w, h, gx, row_y(1), ld_stream(fin + row_y(1) * w + gx));
+#endif
     float2 fq[TF_FQ];            // flows of rows i+PF .. i+PF+FQ-1 (a DRAM round trip ahead of their use)
 #pragma unroll
     for (int j = 0; j < TF_FQ; ++j) fq[j] = ld_stream(fin + row_y(TF_PF + j) * w + gx);
@@ -276,9 +360,20 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
         for (int j = 0; j < IT_RB; ++j) {
             const int i = b * IT_RB + j;
             // prefetch: the next row's taps (its flow was requested four rows ago) and the flow of row i+5
+#if TF_DEEP
+            // blend this row's taps, then immediately re-issue the same registers for row i + 2: two rows of gathers in
+            // flight per thread with two register sets (the loads of row i + 1 were issued one row ago)
+            Taps& st = (j & 1) ? cur1 : cur;
+            float rbl[5];
+            const int y_cur = row_y(i);
+            blend_taps<true>(st, rbl, w, h, gx, y_cur);
+            issue_taps(st, RP, w, h, gx, row_y(i + TF_PF), fq[j % TF_FQ]);
+            fq[j % TF_FQ] = ld_stream(fin + row_y(i + TF_PF + TF_FQ) * w + gx);
+#else
             Taps nxt;
             issue_taps(nxt, RP, w, h, gx, row_y(i + TF_PF), fq[j % TF_FQ]);
             fq[j % TF_FQ] = ld_stream(fin + row_y(i + TF_PF + TF_FQ) * w + gx);
+#endif
             if (IT_PREFETCH_ROWS > 0) {
                 // pull the R rows this column will gather from a few rows later into L2 (both images: R0 and R1)
                 const int op = row_y(i + IT_PREFETCH_ROWS) * w + gx;
@@ -287,7 +382,31 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
                 if ((tid & 3) == 0) { prefetch_l2(RP.R1b + op); prefetch_l2(RP.R0b + op); }
             }
             float m[5];
+#if TF_DEEP
+            matrix_from_blend(rbl, y_cur, h, sc_x, m);
+#else
             matrix_from_taps(cur, h, sc_x, m);
+#endif
+            if constexpr (TM) {
+                // same arithmetic, the ring slot in tensor memory: consume P_{j-1} of batch b-3, fetch its P_j (async),
+                // write the vertical sums, then overwrite the slot with this batch's P_j
+                float xold[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    P[k] = (j == 0) ? m[k] : P[k] + m[k];
+                    xold[k] = B3[k];
+                    if (j > 0) xold[k] -= pold[k];
+                }
+                const uint32_t slot = tm_base + (uint32_t)((rb * 3 + j) * 5);
+                if (j < IT_RB - 1) tm_ld5(pold, slot);
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+                    vbm[(j * 5 + k) * C::VP + C::VPAD + tid] = (xold[k] + B2[k]) + (B1[k] + P[k]);
+                if (j < IT_RB - 1) {
+                    tm_wait_ld();
+                    tm_st5(slot, P);
+                }
+            } else {
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
                 P[k] = (j == 0) ? m[k] : P[k] + m[k];
@@ -300,7 +419,10 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
                 }
                 vbm[(j * 5 + k) * C::VP + C::VPAD + tid] = (xold + B2[k]) + (B1[k] + P[k]);
             }
+            }
+#if !TF_DEEP
             cur = nxt;
+#endif
         }
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
@@ -309,6 +431,7 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
             B1[k] = P[k];
         }
         rb = (rb == 2) ? 0 : rb + 1;
+        if constexpr (TM) tm_wait_st();
         if (HK == 8 && (b & 1) == 0 && b + 1 < n_batches) continue;   // H phase after every second batch
         __syncthreads();
         // ---- H phase: row hr of the H batch, outputs HK*cg .. HK*cg+HK-1 ---------------------------------------
@@ -316,6 +439,12 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
         const int y = r_begin + hb0 * IT_RB + hr - IT_HALO;
         if (y >= yc0 && y < yc1 && (HK == 4 || hr < IT_RB * (b - hb0 + 1))) {
             float g[5][HK];
+            if (TF_ABL == 3) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+#pragma unroll
+                    for (int i = 0; i < HK; ++i) g[k][i] = 0.f;
+            } else
             if constexpr (HS) {
                 // a warp owns the whole row (NT / HK == 32): every lane reads only its own quad of vertical sums and the
                 // window halves come from the neighbouring lanes as prefix / suffix / full quad sums
@@ -388,18 +517,21 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
         if (HK == 8) __syncthreads();   // single vertical-sum buffer: the next M batch overwrites it
     }
     }   // segments
+    if constexpr (TM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid < 32)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "n"(C::TM_COLS) : "memory");
+    }
 }
 
-template <int NT, int HK, bool HS = false>
+template <int NT, int HK, bool HS = false, bool TM = false>
 static void launch_strip(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride,
                          float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, float clamp, cudaStream_t s) {
-    using C = StripCfg<NT, HK, HS>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(fb_iter_strip_kernel<NT, HK, HS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        cudaFuncSetAttribute(fb_iter_strip_kernel<NT, HK, HS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        attr_set = true;
-    }
+    using C = StripCfg<NT, HK, HS, TM>;
+    // (the attribute is per device: set it on every call, it is cheap)
+    cudaFuncSetAttribute(fb_iter_strip_kernel<NT, HK, HS, true, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaFuncSetAttribute(fb_iter_strip_kernel<NT, HK, HS, false, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     const int strips = cdiv(w, C::OUT_W);
     const long long slots = 148LL * (NT == 256 ? 2 : (HS ? TF_HS_CTAS : 4));
     static const char* env_persist = getenv("TF_PERSIST");
@@ -412,7 +544,7 @@ static void launch_strip(const float* R, long long img_stride, const float* flow
         // CTA still gets at least 24 rows so the warm-up rows do not dominate
         const int span = (int)max((total + slots / 2 - 1) / (slots / 2), 24LL);
         const int n_cta_pairs = (int)((total + span - 1) / span);
-        fb_iter_strip_kernel<NT, HK, HS, true><<<2 * n_cta_pairs, NT, C::SMEM_BYTES, s>>>(
+        fb_iter_strip_kernel<NT, HK, HS, true, TM><<<2 * n_cta_pairs, NT, C::SMEM_BYTES, s>>>(
             R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, h, w, 0, clamp, strips, span, (int)total);
         return;
     }
@@ -429,11 +561,368 @@ static void launch_strip(const float* R, long long img_stride, const float* flow
     for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
         const int np = min(n_pairs - p0, 65535);
         dim3 g(2 * strips, chunks, np);
-        fb_iter_strip_kernel<NT, HK, HS, false><<<g, NT, C::SMEM_BYTES, s>>>(R + (long long)(2 * p0) * img_stride, img_stride,
+        fb_iter_strip_kernel<NT, HK, HS, false, TM><<<g, NT, C::SMEM_BYTES, s>>>(R + (long long)(2 * p0) * img_stride, img_stride,
                                                               flow_in + (long long)(2 * p0) * 2 * h * w,
                                                               out_fwd + p0 * fwd_stride, fwd_stride,
                                                               out_bwd + p0 * bwd_stride, bwd_stride, h, w, chunk_rows, clamp,
                                                               strips, 0, 0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// TMA-staged variant (the default): same strip march, same arithmetic (bit-identical results), but
+//   * the address-regular streams of a strip -- R0 (float4 + float) and the flow, 28 of the 48 bytes a pixel reads --
+//     are staged a batch (4 rows) ahead into shared memory by bulk async copies (cp.async.bulk, TMA engine, one
+//     mbarrier per ring slot).  They no longer occupy LSU issue slots, L1 miss-queue entries, scoreboards or
+//     destination registers (the flow queue and the R0 halves of both tap sets are gone), and their lookahead is a
+//     whole batch instead of one row;
+//   * the prefix-sum ring of the vertical window lives in tensor memory (LDTM / STTM instead of shared-memory
+//     wavefronts), which is what frees the shared memory for the staging ring at 4 CTAs per SM;
+//   * the R1 bilinear gather stays on the L1-cached LDG path (its addresses depend on the flow), PF rows ahead.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct TsCfg {
+    static constexpr int NT = 128, HK = 4, OUT_W = NT - 2 * IT_HALO, SLOTS = 2;
+    static constexpr int A_ROW = NT * 16;                    // R0 float4 plane: bytes per staged row
+    static constexpr int B_ROW = (NT + 4) * 4;               // R0 c4 plane (+ up to 3 floats of alignment skew)
+    static constexpr int F_ROW = (NT + 2) * 8;               // flow (+ 1 float2 of alignment skew)
+    static constexpr int A_OFF = 0, B_OFF = IT_RB * A_ROW, F_OFF = B_OFF + IT_RB * B_ROW;
+    static constexpr int SLOT_BYTES = F_OFF + IT_RB * F_ROW;
+    static constexpr int VBUF_FLOATS = 8 * 5 * NT;
+    static constexpr int VBUF_OFF = SLOTS * SLOT_BYTES;
+    static constexpr int MBAR_OFF = VBUF_OFF + VBUF_FLOATS * 4;
+    static constexpr int SMEM_BYTES = MBAR_OFF + SLOTS * 8;
+    static constexpr int TM_COLS = 64;
+    static_assert(A_ROW % 16 == 0 && B_ROW % 16 == 0 && F_ROW % 16 == 0 && SLOT_BYTES % 16 == 0, "bulk copies: 16-byte granules");
+};
+
+// the R1 half of a pixel's reads (R0 and the flow come from the staging ring)
+struct TapsR1 {
+    float4 p00, p01, p10, p11;
+    float q00, q01, q10, q11;
+    float dx, dy;
+};
+
+__device__ __forceinline__ void issue_taps_r1(TapsR1& t, const float4* __restrict__ R1a, const float* __restrict__ R1b,
+                                              int w, int h, int x, int y, float2 f) {
+    t.dx = f.x;
+    t.dy = f.y;
+    const float fx = (float)x + f.x, fy = (float)y + f.y;
+    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+    const int xc = max(min(x1, w - 2), 0), yc = max(min(y1, h - 2), 0);
+    const float4* a0 = R1a + (yc * w + xc);
+    const float4* a1 = a0 + w;
+    const float* b0 = R1b + (yc * w + xc);
+    const float* b1 = b0 + w;
+    t.p00 = __ldg(a0);
+    t.p01 = __ldg(a0 + 1);
+    t.p10 = __ldg(a1);
+    t.p11 = __ldg(a1 + 1);
+    t.q00 = __ldg(b0);
+    t.q01 = __ldg(b0 + 1);
+    t.q10 = __ldg(b1);
+    t.q11 = __ldg(b1 + 1);
+}
+
+// FarnebackUpdateMatrices part 1 (same arithmetic as blend_taps): taps + R0 (c, c4) -> r2..r6 before border scaling
+__device__ __forceinline__ void blend_r1(const TapsR1& t, float4 c, float c4, int w, int h, int x, int y, float r[5]) {
+    float fx = (float)x + t.dx, fy = (float)y + t.dy;
+    const float flx = floorf(fx), fly = floorf(fy);
+    const bool inside = (unsigned)(int)flx < (unsigned)(w - 1) && (unsigned)(int)fly < (unsigned)(h - 1);
+    fx -= flx; fy -= fly;
+    float r2, r3, r4, r5, r6;
+    if (inside) {
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        r2 = a00 * t.p00.x + a01 * t.p01.x + a10 * t.p10.x + a11 * t.p11.x;
+        r3 = a00 * t.p00.y + a01 * t.p01.y + a10 * t.p10.y + a11 * t.p11.y;
+        r4 = a00 * t.p00.z + a01 * t.p01.z + a10 * t.p10.z + a11 * t.p11.z;
+        r5 = a00 * t.p00.w + a01 * t.p01.w + a10 * t.p10.w + a11 * t.p11.w;
+        r6 = a00 * t.q00 + a01 * t.q01 + a10 * t.q10 + a11 * t.q11;
+        r4 = (c.z + r4) * 0.5f;
+        r5 = (c.w + r5) * 0.5f;
+        r6 = (c4 + r6) * 0.25f;
+    } else {
+        r2 = r3 = 0.f;
+        r4 = c.z;
+        r5 = c.w;
+        r6 = c4 * 0.5f;
+    }
+    r2 = (c.x - r2) * 0.5f;
+    r3 = (c.y - r3) * 0.5f;
+    r2 += r4 * t.dy + r6 * t.dx;
+    r3 += r6 * t.dy + r5 * t.dx;
+    r[0] = r2; r[1] = r3; r[2] = r4; r[3] = r5; r[4] = r6;
+}
+
+template <int PF>
+__global__ void __launch_bounds__(TsCfg::NT, 4)
+fb_iter_tma_kernel(const float* __restrict__ R, long long img_stride, const float* __restrict__ flow_in,
+                   float* __restrict__ out_fwd, long long fwd_stride, float* __restrict__ out_bwd, long long bwd_stride,
+                   int h, int w, int chunk_rows, float clampv) {
+    using C = TsCfg;
+    constexpr int NT = C::NT, HK = C::HK;
+    static_assert(PF == 1 || PF == 2, "rows of R1 taps in flight");
+    extern __shared__ __align__(128) unsigned char ts_smem[];
+    float* vbuf = reinterpret_cast<float*>(ts_smem + C::VBUF_OFF);     // [buf][row][k][NT]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(ts_smem + C::MBAR_OFF);
+    __shared__ uint32_t tm_addr_s;
+    const int tid = threadIdx.x;
+    const int dir = blockIdx.x & 1, strip = blockIdx.x >> 1, pair = blockIdx.z;
+    const int yc0 = blockIdx.y * chunk_rows, yc1 = min(yc0 + chunk_rows, h);
+    const int plane = h * w;
+    const float* Rp = R + (long long)(2 * pair) * img_stride;
+    const float* Rn = Rp + img_stride;
+    const float* R0 = dir ? Rn : Rp;
+    const float* R1 = dir ? Rp : Rn;
+    const float4* R0a = reinterpret_cast<const float4*>(R0);
+    const float* R0b = R0 + 4 * (long long)plane;
+    const float4* R1a = reinterpret_cast<const float4*>(R1);
+    const float* R1b = R1 + 4 * (long long)plane;
+    const float2* fin = reinterpret_cast<const float2*>(flow_in) + (long long)(2 * pair + dir) * plane;
+    float2* fout = reinterpret_cast<float2*>(dir ? out_bwd + (long long)pair * bwd_stride
+                                                 : out_fwd + (long long)pair * fwd_stride);
+    const int x0 = strip * C::OUT_W;
+    const int xs = x0 - IT_HALO;                                  // image column of region column 0
+    const int cx0 = max(xs, 0), cx1 = min(xs + NT, w), ncol = cx1 - cx0;   // staged (in-image) columns
+    const int gx = min(max(xs + tid, 0), w - 1);                  // this thread's column, replicate-clamped
+    const int gxs = gx - cx0;                                     // its index inside the staged columns
+    const float sc_x = border_factor(gx, w);
+    const int hr = tid >> 5, cg = tid & 31;
+    // alignment skews of the 4-byte / 8-byte streams (bulk copies move 16-byte granules from 16-byte-aligned addresses)
+    const unsigned skb0 = (unsigned)(reinterpret_cast<uintptr_t>(R0b) >> 2), skf0 = (unsigned)(reinterpret_cast<uintptr_t>(fin) >> 3);
+
+    // tensor memory for the prefix-sum ring, barriers of the staging ring
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tm_addr_s)), "n"(C::TM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (tid == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm_base = tm_addr_s + ((uint32_t)(tid >> 5) << 21);
+    {
+        const float z[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int s = 0; s < 9; ++s) tm_st5(tm_base + 5 * s, z);
+        tm_wait_st();
+    }
+    float B1[5], B2[5], B3[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) B1[k] = B2[k] = B3[k] = 0.f;
+    const int r_begin = (((yc0 - IT_HALO + 8) >> 2) << 2) - 8;
+    const int n_rows = (yc1 + IT_HALO) - r_begin;
+    const int n_batches = (n_rows + IT_RB - 1) / IT_RB;
+    int rb = 0;
+    auto row_y = [&](int i) { return min(max(r_begin + i, 0), h - 1); };
+
+    // warp 0: stage batch bb (rows 4bb .. 4bb+3, replicate-clamped) into ring slot bb & 1: lane 3r + kind copies one
+    // row of one stream; lane 0 arms the slot's barrier with the byte total first
+    auto stage_batch = [&](int bb) {
+        const int lane = tid;
+        const int r = lane / 3, kind = lane - 3 * r;
+        unsigned char* slot = ts_smem + (bb & 1) * C::SLOT_BYTES;
+        uint64_t* bar = &mbar[bb & 1];
+        const void* src = nullptr;
+        void* dst = nullptr;
+        uint32_t bytes = 0;
+        if (lane < 3 * IT_RB) {
+            const int y = row_y(IT_RB * bb + r);
+            const int e = y * w + cx0;
+            if (kind == 0) {
+                src = R0a + e;
+                dst = slot + C::A_OFF + r * C::A_ROW + (cx0 - xs) * 16;
+                bytes = (uint32_t)ncol * 16u;
+            } else if (kind == 1) {
+                const unsigned sk = (skb0 + (unsigned)e) & 3u;
+                src = R0b + e - sk;
+                dst = slot + C::B_OFF + r * C::B_ROW;
+                bytes = ((sk + (unsigned)ncol + 3u) & ~3u) * 4u;
+            } else {
+                const unsigned sk = (skf0 + (unsigned)e) & 1u;
+                src = fin + e - sk;
+                dst = slot + C::F_OFF + r * C::F_ROW;
+                bytes = ((sk + (unsigned)ncol + 1u) & ~1u) * 8u;
+            }
+        }
+        uint32_t total = bytes;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        if (lane == 0) mbar_arrive_expect_tx(bar, total);
+        __syncwarp();
+        if (bytes) bulk_g2s(dst, src, bytes, bar);
+    };
+    // this thread's staged values of row (bb, j)
+    auto staged_flow = [&](int bb, int j) {
+        const int y = row_y(IT_RB * bb + j);
+        const unsigned sk = (skf0 + (unsigned)(y * w + cx0)) & 1u;
+        return reinterpret_cast<const float2*>(ts_smem + (bb & 1) * C::SLOT_BYTES + C::F_OFF + j * C::F_ROW)[sk + gxs];
+    };
+
+    if (tid < 32) {
+        stage_batch(0);
+        if (n_batches > 1) stage_batch(1);
+    }
+    mbar_wait(&mbar[0], 0u);
+    TapsR1 S0, S1;                                               // PF == 1: S0 = current row, S1 = next row
+    issue_taps_r1(S0, R1a, R1b, w, h, gx, row_y(0), staged_flow(0, 0));
+    if (PF == 2) issue_taps_r1(S1, R1a, R1b, w, h, gx, row_y(1), staged_flow(0, 1));
+
+    for (int b = 0; b < n_batches; ++b) {
+        float* vbm = vbuf + (b & 1) * (IT_RB * 5 * NT);
+        const unsigned char* slot = ts_smem + (b & 1) * C::SLOT_BYTES;
+        float P[5], pold[5];
+#pragma unroll
+        for (int j = 0; j < IT_RB; ++j) {
+            const int i = b * IT_RB + j;
+            const int y_cur = row_y(i);
+            // R0 of this row from the staging ring
+            const float4 c = reinterpret_cast<const float4*>(slot + C::A_OFF + j * C::A_ROW)[gx - xs];
+            const unsigned skb = (skb0 + (unsigned)(y_cur * w + cx0)) & 3u;
+            const float c4 = reinterpret_cast<const float*>(slot + C::B_OFF + j * C::B_ROW)[skb + gxs];
+            // the flow of row i + PF (the next batch's slot from row 4 - PF on: its copies were issued a batch ago)
+            const int jn = j + PF;
+            const int bn = b + (jn >= IT_RB ? 1 : 0);
+            if (jn == IT_RB && bn < n_batches) mbar_wait(&mbar[bn & 1], (uint32_t)((bn >> 1) & 1));
+            float2 fnext = make_float2(0.f, 0.f);
+            if (bn < n_batches) fnext = staged_flow(bn, jn & (IT_RB - 1));
+            float rbl[5];
+            if (PF == 1) {
+                issue_taps_r1(S1, R1a, R1b, w, h, gx, row_y(i + 1), fnext);
+                blend_r1(S0, c, c4, w, h, gx, y_cur, rbl);
+            } else {
+                TapsR1& st = (j & 1) ? S1 : S0;
+                blend_r1(st, c, c4, w, h, gx, y_cur, rbl);
+                issue_taps_r1(st, R1a, R1b, w, h, gx, row_y(i + 2), fnext);
+            }
+            float m[5];
+            matrix_from_blend(rbl, y_cur, h, sc_x, m);
+            float xold[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                P[k] = (j == 0) ? m[k] : P[k] + m[k];
+                xold[k] = B3[k];
+                if (j > 0) xold[k] -= pold[k];
+            }
+            const uint32_t tslot = tm_base + (uint32_t)((rb * 3 + j) * 5);
+            if (j < IT_RB - 1) tm_ld5(pold, tslot);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) vbm[(j * 5 + k) * NT + tid] = (xold[k] + B2[k]) + (B1[k] + P[k]);
+            if (j < IT_RB - 1) {
+                tm_wait_ld();
+                tm_st5(tslot, P);
+            }
+            if (PF == 1) S0 = S1;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            B3[k] = B2[k];
+            B2[k] = B1[k];
+            B1[k] = P[k];
+        }
+        rb = (rb == 2) ? 0 : rb + 1;
+        tm_wait_st();
+        __syncthreads();
+        // every thread is done with slot b & 1: refill it with batch b + 2
+        if (tid < 32 && b + 2 < n_batches) stage_batch(b + 2);
+        // ---- H phase: a warp owns row hr of the batch, a lane four adjacent outputs ---------------------------------
+        const int y = r_begin + b * IT_RB + hr - IT_HALO;
+        if (y >= yc0 && y < yc1) {
+            float g[5][HK];
+            constexpr unsigned FULL = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const float4 q = *reinterpret_cast<const float4*>(vbm + (hr * 5 + k) * NT + HK * cg);
+                const float p2 = q.x + q.y, s2 = q.z + q.w;
+                const float T = p2 + s2, p3 = p2 + q.z, s3 = q.y + s2;
+                const float Tm1 = __shfl_up_sync(FULL, T, 1), Tp1 = __shfl_down_sync(FULL, T, 1);
+                const float s2m2 = __shfl_up_sync(FULL, s2, 2), s1m2 = __shfl_up_sync(FULL, q.w, 2);
+                const float s3m1 = __shfl_up_sync(FULL, s3, 1), p3p1 = __shfl_down_sync(FULL, p3, 1);
+                const float p1p2 = __shfl_down_sync(FULL, q.x, 2), p2p2 = __shfl_down_sync(FULL, p2, 2);
+                const float U = Tm1 + T;
+                g[k][0] = (s2m2 + U) + p3p1;
+                g[k][1] = (s1m2 + U) + Tp1;
+                g[k][2] = (U + Tp1) + p1p2;
+                g[k][3] = (s3m1 + T) + (Tp1 + p2p2);
+            }
+            const float reg = 1e-3f * (float)(IT_WIN * IT_WIN) * (float)(IT_WIN * IT_WIN);
+            float2 o[HK];
+#pragma unroll
+            for (int i = 0; i < HK; ++i) {
+                const float g11 = g[0][i], g12 = g[1][i], g22 = g[2][i];
+                const float h1 = g[3][i], h2 = g[4][i];
+                const float idet = 1.f / (diff_of_products(g11, g22, g12, g12) + reg);
+                float fx = diff_of_products(g11, h2, g12, h1) * idet;
+                float fy = diff_of_products(g22, h1, g12, h2) * idet;
+                if (clampv > 0.f) {
+                    fx = fminf(fmaxf(fx, -clampv), clampv);
+                    fy = fminf(fmaxf(fy, -clampv), clampv);
+                }
+                o[i] = make_float2(fx, fy);
+            }
+            const int c0 = HK * cg;
+            const int xg = xs + c0;
+            float2* dst = fout + (long long)y * w + xg;
+#pragma unroll
+            for (int i = 0; i < HK; ++i) {
+                const int cc = c0 + i;
+                if (cc >= IT_HALO && cc < NT - IT_HALO && xg + i < w) dst[i] = o[i];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_addr_s), "n"(C::TM_COLS) : "memory");
+}
+
+template <int PF>
+static void launch_tma(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride,
+                       float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, float clamp, cudaStream_t s) {
+    using C = TsCfg;
+    cudaFuncSetAttribute(fb_iter_tma_kernel<PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    const int strips = cdiv(w, C::OUT_W);
+    const long long slots = 148LL * 4;
+    // rows per chunk: minimise (waves of resident CTAs) x (rows a CTA marches, incl. its 12 warm-up rows)
+    int chunks = 1;
+    long long best = -1;
+    for (int c = 1; c <= max(1, h / 16); ++c) {
+        const long long ctas = 2LL * strips * c * n_pairs;
+        const long long cost = ((ctas + slots - 1) / slots) * (cdiv(h, c) + 2 * IT_HALO);
+        if (best < 0 || cost < best) { best = cost; chunks = c; }
+    }
+    const int chunk_rows = cdiv(h, chunks);
+    chunks = cdiv(h, chunk_rows);
+    for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
+        const int np = min(n_pairs - p0, 65535);
+        dim3 g(2 * strips, chunks, np);
+        fb_iter_tma_kernel<PF><<<g, C::NT, C::SMEM_BYTES, s>>>(R + (long long)(2 * p0) * img_stride, img_stride,
+                                                              flow_in + (long long)(2 * p0) * 2 * h * w,
+                                                              out_fwd + p0 * fwd_stride, fwd_stride,
+                                                              out_bwd + p0 * bwd_stride, bwd_stride, h, w, chunk_rows, clamp);
     }
 }
 
@@ -454,6 +943,16 @@ int launch_fb_iteration(const float* R, long long img_stride, const float* flow_
     // more independent CTAs hide each other's barrier and gather latency.  256 only when it wastes clearly less.
     static const char* force_hs = getenv("TF_HSHFL");
     const bool hshfl = force_hs ? (atoi(force_hs) != 0) : true;
+    // TMA-staged kernel: needs 16-byte-aligned float4 planes / flow rows are handled by skews; 2-px-wide levels are not
+    static const char* force_tma = getenv("TF_TMA");
+    const int tma = force_tma ? atoi(force_tma) : 0;
+    if (tma && w >= 2 && h >= 2) {
+        if (tma == 2) launch_tma<2>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
+        else launch_tma<1>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
+        return check_launch("fb iteration (tma)");
+    }
+    static const char* force_tm = getenv("TF_TMEM");
+    const bool tmem = force_tm ? (atoi(force_tm) != 0) : false;
     static const char* force_nt = getenv("TF_FORCE_NT");
     const bool use256 = force_nt ? (atoi(force_nt) == 256) : (10 * pad256 < 9 * pad128);
     if (use256 && hk8)
@@ -462,6 +961,8 @@ int launch_fb_iteration(const float* R, long long img_stride, const float* flow_
         launch_strip<256, 4>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
     else if (hk8)
         launch_strip<128, 8>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
+    else if (hshfl && tmem)
+        launch_strip<128, 4, true, true>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
     else if (hshfl)
         launch_strip<128, 4, true>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
     else

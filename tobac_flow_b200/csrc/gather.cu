@@ -616,10 +616,16 @@ extern "C" int tf_flow_finalise(float* fwd, float* bwd, int T, int H, int W, flo
     } else {
         // only the two end frames change
         dim3 grid((unsigned)((fe + 255) / 256), 1);
-        if (mirror_first)
-            flow_finalise_kernel<<<grid, 256, 0, s>>>(fwd, bwd, T == 1 ? 1 : 2, fe, 0.f, 0, 1, T == 1 && mirror_last);
-        if (mirror_last && T > 1)
-            flow_finalise_kernel<<<grid, 256, 0, s>>>(fwd + (T - 1) * fe, bwd + (T - 1) * fe, 1, fe, 0.f, 0, 0, 1);
+        if (T == 1) {
+            // a one-frame shard: frame 0 is both ends (either rule may apply alone, e.g. the last rank of a sharded run)
+            if (mirror_first || mirror_last)
+                flow_finalise_kernel<<<grid, 256, 0, s>>>(fwd, bwd, 1, fe, 0.f, 0, mirror_first, mirror_last);
+        } else {
+            if (mirror_first)
+                flow_finalise_kernel<<<grid, 256, 0, s>>>(fwd, bwd, 2, fe, 0.f, 0, 1, 0);
+            if (mirror_last)
+                flow_finalise_kernel<<<grid, 256, 0, s>>>(fwd + (T - 1) * fe, bwd + (T - 1) * fe, 1, fe, 0.f, 0, 0, 1);
+        }
     }
     return check_launch("tf_flow_finalise");
 }

@@ -229,6 +229,140 @@ __global__ void __launch_bounds__(256) blur3_resize_kernel(const uint8_t* __rest
     out[((long long)img * h + j) * w + i] = r0 * (1.f - fy) + r1 * fy;
 }
 
+// Down-sampled level in ONE pass (any blur width): a CTA owns a TW x TH tile of the level image.
+//   1. the u8 footprint of the tile (REFLECT_101 applied while loading) goes to shared memory;
+//   2. vertical blur at the two source rows of every destination row, 4 columns per thread, the two rows sharing one
+//      walk over ksize + 1 footprint rows (they are neighbours; at the bottom clamp they coincide);
+//   3. horizontal blur at the two source columns of every destination pixel + OpenCV's bilinear weights.
+// Same arithmetic, in the same order, as the two-pass kernels above (fp32, taps accumulated in k order), but nothing
+// round-trips through HBM and the image rows come from shared memory instead of L2.  The rows of vertical sums are
+// skewed by one float per 32 columns so that the stride-`scale` reads of step 3 are bank-conflict free.
+__device__ __forceinline__ int skew32(int c) { return c + (c >> 5); }
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(256) blur_resize_tile_kernel(const uint8_t* __restrict__ q0, const uint8_t* __restrict__ q1,
+                                                               float* __restrict__ out, int H, int W, int h, int w,
+                                                               double scale_x, double scale_y, int FWp, int FH,
+                                                               BlurTaps taps) {
+    extern __shared__ __align__(16) unsigned char pyr_smem[];
+    const int VP = skew32(FWp) + 1;                              // pitch of a row of vertical sums
+    unsigned* foot = reinterpret_cast<unsigned*>(pyr_smem);      // [FH][FWp / 4] words of 4 pixels
+    float* V = reinterpret_cast<float*>(pyr_smem + (size_t)FH * FWp);   // [2 * TH][VP]
+    const int tid = threadIdx.x;
+    const int img = blockIdx.z;
+    const uint8_t* src = ((img & 1) ? q1 : q0) + (long long)(img >> 1) * H * W;
+    const int i0 = blockIdx.x * TW, j0 = blockIdx.y * TH;
+    const int ni = min(TW, w - i0), nj = min(TH, h - j0);
+    const int rad = taps.ksize >> 1;
+    int xa, ya, t0, t1; float tf;
+    resize_coord(i0, scale_x, W, xa, t1, tf);
+    resize_coord(j0, scale_y, H, ya, t1, tf);
+    xa -= rad; ya -= rad;
+    const int xal = xa & ~3;                                     // footprint starts at a 4-pixel boundary (may be < 0)
+    resize_coord(i0 + ni - 1, scale_x, W, t0, t1, tf);
+    const int fw4 = min((t1 + rad - xal) / 4 + 1, FWp / 4);      // words per footprint row actually needed
+    resize_coord(j0 + nj - 1, scale_y, H, t0, t1, tf);
+    const int fh = min(t1 + rad - ya + 1, FH);
+    const int W4 = FWp >> 2;
+
+    // 1. footprint
+    const bool rows_aligned = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0;
+    for (int idx = tid; idx < fh * fw4; idx += 256) {
+        const int r = idx / fw4, c4 = idx - r * fw4;
+        const int gy = reflect101(ya + r, H);
+        const int gx = xal + 4 * c4;
+        const uint8_t* row = src + (long long)gy * W;
+        unsigned v;
+        if (rows_aligned && gx >= 0 && gx + 3 < W) {
+            v = __ldg(reinterpret_cast<const unsigned*>(row + gx));
+        } else {
+            v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v |= (unsigned)__ldg(row + reflect101(gx + b, W)) << (8 * b);
+        }
+        foot[r * W4 + c4] = v;
+    }
+    __syncthreads();
+
+    // 2. vertical blur: task = (destination row, 4 columns)
+    for (int idx = tid; idx < nj * fw4; idx += 256) {
+        const int j = idx / fw4, c4 = idx - j * fw4;
+        int y0, y1; float fy;
+        resize_coord(j0 + j, scale_y, H, y0, y1, fy);
+        const unsigned* p = foot + (y0 - rad - ya) * W4 + c4;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        if (y1 == y0 + 1) {
+            float wprev = 0.f;
+#pragma unroll 4
+            for (int k = 0; k <= taps.ksize; ++k) {
+                const unsigned c = p[k * W4];
+                const float wk = k < taps.ksize ? taps.w[k] : 0.f;
+                const float v0 = byte_to_float(c, 0x7540u), v1 = byte_to_float(c, 0x7541u);
+                const float v2 = byte_to_float(c, 0x7542u), v3 = byte_to_float(c, 0x7543u);
+                a0.x += wk * v0; a0.y += wk * v1; a0.z += wk * v2; a0.w += wk * v3;
+                a1.x += wprev * v0; a1.y += wprev * v1; a1.z += wprev * v2; a1.w += wprev * v3;
+                wprev = wk;
+            }
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < taps.ksize; ++k) {
+                const unsigned c = p[k * W4];
+                const float wk = taps.w[k];
+                a0.x += wk * byte_to_float(c, 0x7540u);
+                a0.y += wk * byte_to_float(c, 0x7541u);
+                a0.z += wk * byte_to_float(c, 0x7542u);
+                a0.w += wk * byte_to_float(c, 0x7543u);
+            }
+            a1 = a0;                                             // y1 == y0: the same source row
+        }
+        float* v0p = V + (2 * j) * VP + skew32(4 * c4);
+        float* v1p = v0p + VP;
+        v0p[0] = a0.x; v0p[1] = a0.y; v0p[2] = a0.z; v0p[3] = a0.w;
+        v1p[0] = a1.x; v1p[1] = a1.y; v1p[2] = a1.z; v1p[3] = a1.w;
+    }
+    __syncthreads();
+
+    // 3. horizontal blur at the two source columns + bilinear weights: one destination pixel per thread
+    for (int idx = tid; idx < nj * TW; idx += 256) {
+        const int j = idx / TW, ii = idx - j * TW;
+        if (ii >= ni) continue;
+        int x0, x1, y0, y1; float fx, fy;
+        resize_coord(i0 + ii, scale_x, W, x0, x1, fx);
+        resize_coord(j0 + j, scale_y, H, y0, y1, fy);
+        const float* row0 = V + (2 * j) * VP;
+        const float* row1 = row0 + VP;
+        const int c0 = x0 - rad - xal;
+        float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+        if (x1 == x0 + 1) {
+            float a0 = row0[skew32(c0)], a1 = row1[skew32(c0)];
+#pragma unroll 4
+            for (int k = 0; k < taps.ksize; ++k) {
+                const float wk = taps.w[k];
+                const int cs = skew32(c0 + k + 1);
+                const float n0 = row0[cs], n1 = row1[cs];
+                b00 += wk * a0;
+                b01 += wk * n0;
+                b10 += wk * a1;
+                b11 += wk * n1;
+                a0 = n0;
+                a1 = n1;
+            }
+        } else {
+            for (int k = 0; k < taps.ksize; ++k) {
+                const float wk = taps.w[k];
+                const int cs = skew32(c0 + k);
+                b00 += wk * row0[cs];
+                b10 += wk * row1[cs];
+            }
+            b01 = b00;                                           // x1 == x0: the same source column
+            b11 = b10;
+        }
+        const float r0 = b00 * (1.f - fx) + b01 * fx;
+        const float r1 = b10 * (1.f - fx) + b11 * fx;
+        out[((long long)img * h + (j0 + j)) * w + (i0 + ii)] = r0 * (1.f - fy) + r1 * fy;
+    }
+}
+
 // pass B at the full-resolution level (w == W, no resize), 4 outputs per thread (W % 4 == 0)
 __global__ void __launch_bounds__(256) blur_h4_fullres_kernel(const float* __restrict__ tmp, float* __restrict__ out, int W,
                                                               int h, BlurTaps taps) {
@@ -358,7 +492,7 @@ __global__ void __launch_bounds__(256) flow_upsample_kernel(const float2* __rest
 }
 
 int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int H, int W, int h, int w, int ksize,
-                         double sigma, float* tmp, float* out, cudaStream_t s) {
+                         double sigma, float* tmp, float* out, cudaStream_t s, bool two_pass) {
     BlurTaps taps;
     taps.ksize = ksize;
     if (ksize > kMaxBlurTaps) { set_error("pyramid: blur kernel too wide (%d)", ksize); return TF_ERR_UNSUPPORTED; }
@@ -378,7 +512,39 @@ int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int 
     const double sx = (double)W / w, sy = (double)H / h;
     const int n_img = 2 * n_pairs;
     static const char* env_two_pass = getenv("TF_PYR_TWO_PASS");
-    const bool fused3 = ksize == 3 && !env_two_pass && ((h == H && w == W && W % 4 == 0) || rp == 2);
+    two_pass = two_pass || env_two_pass != nullptr;
+    if (rp == 2 && !two_pass) {
+        // one fused pass per down-sampled level; tile shape by down-sampling factor (bigger footprints, smaller tiles)
+        const int n_launch = cdiv(n_img, 65534);
+        LaunchTimer lt(KC_PYRAMID, (2.0 * H * W + 8.0 * h * w) * n_pairs, s, n_launch);
+        const bool wide = sx < 3.0;                              // half resolution: 64 x 16 tiles, else 32 x 8 / 16 x 8 / 8 x 4
+        const int TW = wide ? 64 : (sx < 6.0 ? 32 : (sx < 24.0 ? 16 : 8));
+        const int TH = wide ? 16 : (sx < 24.0 ? 8 : 4);
+        const int FWp = (((int)ceil((TW - 1) * sx) + 2 + ksize + 3 + 3) / 4 + 1) * 4;   // + alignment slack
+        const int FH = (int)ceil((TH - 1) * sy) + 3 + ksize;
+        const size_t smem = (size_t)FH * FWp + (size_t)2 * TH * (FWp + FWp / 32 + 2) * sizeof(float);
+        if (smem <= 200 * 1024) {
+            for (int z0 = 0; z0 < n_img; z0 += 65534) {
+                const int nz = min(n_img - z0, 65534);
+                const uint8_t* a0 = q0 + (long long)(z0 / 2) * H * W;
+                const uint8_t* a1 = q1 + (long long)(z0 / 2) * H * W;
+                float* oz = out + (long long)z0 * h * w;
+                dim3 g(cdiv(w, TW), cdiv(h, TH), nz);
+#define TF_TILE_LAUNCH(TW_, TH_)                                                                                       \
+    do {                                                                                                               \
+        cudaFuncSetAttribute(blur_resize_tile_kernel<TW_, TH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        blur_resize_tile_kernel<TW_, TH_><<<g, 256, smem, s>>>(a0, a1, oz, H, W, h, w, sx, sy, FWp, FH, taps);         \
+    } while (0)
+                if (TW == 64) TF_TILE_LAUNCH(64, 16);
+                else if (TW == 32) TF_TILE_LAUNCH(32, 8);
+                else if (TW == 16) TF_TILE_LAUNCH(16, 8);
+                else TF_TILE_LAUNCH(8, 4);
+#undef TF_TILE_LAUNCH
+            }
+            return check_launch("pyramid level (tile)");
+        }
+    }
+    const bool fused3 = ksize == 3 && !two_pass && ((h == H && w == W && W % 4 == 0) || rp == 2);
     LaunchTimer lt(KC_PYRAMID, (2.0 * H * W + 8.0 * h * w) * n_pairs, s, (fused3 ? 1 : 2) * cdiv(n_img, 65534));
     for (int z0 = 0; z0 < n_img; z0 += 65534) {
         const int nz = min(n_img - z0, 65534);  // even, so image parity is preserved

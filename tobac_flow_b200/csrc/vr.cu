@@ -325,11 +325,8 @@ extern "C" int tf_variational_refinement(const uint8_t* q0, const uint8_t* q1, f
         return TF_ERR_WORKSPACE_TOO_SMALL;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(vr_sor_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM_BYTES);
-        attr_set = true;
-    }
+    // the attribute is per device (a process may drive several): set it on every call, it is cheap
+    cudaFuncSetAttribute(vr_sor_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VS_SMEM_BYTES);
     VrArgs a{};
     a.q0 = q0; a.q1 = q1; a.fwd = fwd; a.fwd_stride = fwd_stride; a.bwd = bwd; a.bwd_stride = bwd_stride;
     a.ws = reinterpret_cast<float*>(workspace); a.H = H; a.W = W;

@@ -689,3 +689,38 @@ def pair_to_8bit(frame0, frame1):
     _lib.check(fn(a.data_ptr(), a.data_ptr() + H * W * a.element_size(), H * W, q.data_ptr(), q.data_ptr() + H * W, 1, H,
                   W, mm.data_ptr(), _stream()), "tf_pair_normalise_u8")
     return (q[0].cpu().numpy(), q[1].cpu().numpy()) if host else (q[0], q[1])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# stage-level entry points (parity tests against the oracle's per-stage restatement of OpenCV's Farneback)
+# ----------------------------------------------------------------------------------------------------------------
+def fb_pyramid_level(q0, q1, level, two_pass=False):
+    """Level image ``level`` (index into ``_lib.level_plan``, coarsest first) of the quantised pair ``q0``, ``q1``
+    ((H, W) uint8 each): convertTo -> GaussianBlur -> resize from the full-resolution image, as
+    ``FarnebackOpticalFlow::calc`` builds it.  Returns (2, h, w) float32 (numpy)."""
+    q = torch.from_numpy(np.ascontiguousarray(np.stack([q0, q1]), dtype=np.uint8)).to(_device())
+    _, H, W = q.shape
+    params = _lib.default_params()
+    h, w = _lib.level_plan(H, W, params)[level]
+    nbytes = _lib.workspace_bytes(1, H, W, params)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=q.device)
+    out = torch.empty((2, h, w), dtype=torch.float32, device=q.device)
+    _lib.check(_lib.load().tf_fb_pyramid_level(q.data_ptr(), q.data_ptr() + H * W, 1, H, W, ctypes.byref(params),
+                                               int(level), out.data_ptr(), ws.data_ptr(), nbytes, int(bool(two_pass)),
+                                               _stream()), "tf_fb_pyramid_level")
+    return out.cpu().numpy()
+
+
+def fb_polyexp(images):
+    """FarnebackPolyExp of (n, h, w) float32 level images -> (n, h, w, 5) float32 (numpy), channels in OpenCV's order."""
+    I = torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32)).to(_device())
+    n, h, w = I.shape
+    params = _lib.default_params()
+    rs = int(_lib.load().tf_fb_r_stride(h, w))
+    R = torch.empty((n, rs), dtype=torch.float32, device=I.device)
+    _lib.check(_lib.load().tf_fb_polyexp(I.data_ptr(), n, h, w, ctypes.byref(params), R.data_ptr(), _stream()),
+               "tf_fb_polyexp")
+    out = torch.empty((n, h, w, 5), dtype=torch.float32, device=I.device)
+    out[..., :4] = R[:, :4 * h * w].reshape(n, h, w, 4)
+    out[..., 4] = R[:, 4 * h * w:5 * h * w].reshape(n, h, w)
+    return out.cpu().numpy()
