@@ -142,7 +142,7 @@ __device__ __forceinline__ void issue_taps(Taps& t, const RPlanes& R, int w, int
 #ifndef TF_ABL
 #define TF_ABL 0     // timing ablations (wrong results): 1 = taps at the undisplaced pixel, 2 = no R1 loads
 #endif
-#if TF_ABL >= 1
+#if TF_ABL >= 1 && TF_ABL <= 3
     const int xc = max(min(x, w - 2), 0), yc = max(min(y, h - 2), 0);
 #else
     const int xc = max(min(x1, w - 2), 0), yc = max(min(y1, h - 2), 0);
@@ -382,7 +382,11 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
                 if ((tid & 3) == 0) { prefetch_l2(RP.R1b + op); prefetch_l2(RP.R0b + op); }
             }
             float m[5];
-#if TF_DEEP
+#if TF_ABL == 4
+            m[0] = cur.p00.x + cur.p01.y + cur.p10.z + cur.p11.w + cur.c.x;
+            m[1] = cur.q00 + cur.q01 + cur.q10 + cur.q11 + cur.c4;
+            m[2] = cur.dx; m[3] = cur.dy; m[4] = cur.c.w;
+#elif TF_DEEP
             matrix_from_blend(rbl, y_cur, h, sc_x, m);
 #else
             matrix_from_taps(cur, h, sc_x, m);
@@ -439,7 +443,7 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
         const int y = r_begin + hb0 * IT_RB + hr - IT_HALO;
         if (y >= yc0 && y < yc1 && (HK == 4 || hr < IT_RB * (b - hb0 + 1))) {
             float g[5][HK];
-            if (TF_ABL == 3) {
+            if (TF_ABL == 3 || TF_ABL == 4) {
 #pragma unroll
                 for (int k = 0; k < 5; ++k)
 #pragma unroll
@@ -503,6 +507,7 @@ fb_iter_strip_kernel(const float* __restrict__ R, long long img_stride, const fl
                     fy = fminf(fmaxf(fy, -clampv), clampv);
                 }
                 o[i] = make_float2(fx, fy);
+                if (TF_ABL == 4) o[i] = make_float2(1.3f + 1e-30f * fx, 0.7f);
             }
             const int c0 = HK * cg;                        // region column of o[0]
             const int xg = x0 - IT_HALO + c0;              // image column of o[0]
@@ -739,41 +744,30 @@ fb_iter_tma_kernel(const float* __restrict__ R, long long img_stride, const floa
     int rb = 0;
     auto row_y = [&](int i) { return min(max(r_begin + i, 0), h - 1); };
 
-    // warp 0: stage batch bb (rows 4bb .. 4bb+3, replicate-clamped) into ring slot bb & 1: lane 3r + kind copies one
-    // row of one stream; lane 0 arms the slot's barrier with the byte total first
+    // Stage batch bb (rows 4bb .. 4bb+3, replicate-clamped) into ring slot bb & 1: warp r copies row r, its lanes 0..2
+    // one stream each (cp.async.bulk takes warp-uniform operands, so the copies of a warp issue one after the other:
+    // three per warp keeps the four warps level at the batch barrier).  Byte counts are constants of the strip -- the
+    // 4-byte / 8-byte streams start at the 16-byte boundary below their first element and always move the padded row
+    // -- so the slot's barrier is armed with a constant by thread 0.
+    const int swarp = tid >> 5, slane = tid & 31;
+    const uint32_t bytes_a = (uint32_t)ncol * 16u, bytes_b = (((uint32_t)ncol + 6u) & ~3u) * 4u,
+                   bytes_f = (((uint32_t)ncol + 2u) & ~1u) * 8u;
+    const uint32_t stage_tx = IT_RB * (bytes_a + bytes_b + bytes_f);
+    const char* st_base = slane == 0 ? reinterpret_cast<const char*>(R0a)
+                        : (slane == 1 ? reinterpret_cast<const char*>(R0b) : reinterpret_cast<const char*>(fin));
+    const int st_esz = slane == 0 ? 16 : (slane == 1 ? 4 : 8);
+    const uint32_t st_bytes = slane == 0 ? bytes_a : (slane == 1 ? bytes_b : bytes_f);
+    const uint32_t st_dst = smem_u32(ts_smem) + (slane == 0 ? C::A_OFF + swarp * C::A_ROW + (cx0 - xs) * 16
+                                                 : (slane == 1 ? C::B_OFF + swarp * C::B_ROW : C::F_OFF + swarp * C::F_ROW));
     auto stage_batch = [&](int bb) {
-        const int lane = tid;
-        const int r = lane / 3, kind = lane - 3 * r;
-        unsigned char* slot = ts_smem + (bb & 1) * C::SLOT_BYTES;
-        uint64_t* bar = &mbar[bb & 1];
-        const void* src = nullptr;
-        void* dst = nullptr;
-        uint32_t bytes = 0;
-        if (lane < 3 * IT_RB) {
-            const int y = row_y(IT_RB * bb + r);
-            const int e = y * w + cx0;
-            if (kind == 0) {
-                src = R0a + e;
-                dst = slot + C::A_OFF + r * C::A_ROW + (cx0 - xs) * 16;
-                bytes = (uint32_t)ncol * 16u;
-            } else if (kind == 1) {
-                const unsigned sk = (skb0 + (unsigned)e) & 3u;
-                src = R0b + e - sk;
-                dst = slot + C::B_OFF + r * C::B_ROW;
-                bytes = ((sk + (unsigned)ncol + 3u) & ~3u) * 4u;
-            } else {
-                const unsigned sk = (skf0 + (unsigned)e) & 1u;
-                src = fin + e - sk;
-                dst = slot + C::F_OFF + r * C::F_ROW;
-                bytes = ((sk + (unsigned)ncol + 1u) & ~1u) * 8u;
-            }
+        const uint32_t bar = smem_u32(&mbar[bb & 1]);
+        if (slane < 3) {
+            const int y = row_y(IT_RB * bb + swarp);
+            const uintptr_t src = (reinterpret_cast<uintptr_t>(st_base) + (long long)(y * w + cx0) * st_esz) & ~(uintptr_t)15;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(st_dst + (uint32_t)(bb & 1) * C::SLOT_BYTES), "l"(src), "r"(st_bytes), "r"(bar) : "memory");
         }
-        uint32_t total = bytes;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-        if (lane == 0) mbar_arrive_expect_tx(bar, total);
-        __syncwarp();
-        if (bytes) bulk_g2s(dst, src, bytes, bar);
+        if (tid == 0) mbar_arrive_expect_tx(&mbar[bb & 1], stage_tx);
     };
     // this thread's staged values of row (bb, j)
     auto staged_flow = [&](int bb, int j) {
@@ -782,10 +776,8 @@ fb_iter_tma_kernel(const float* __restrict__ R, long long img_stride, const floa
         return reinterpret_cast<const float2*>(ts_smem + (bb & 1) * C::SLOT_BYTES + C::F_OFF + j * C::F_ROW)[sk + gxs];
     };
 
-    if (tid < 32) {
-        stage_batch(0);
-        if (n_batches > 1) stage_batch(1);
-    }
+    stage_batch(0);
+    if (n_batches > 1) stage_batch(1);
     mbar_wait(&mbar[0], 0u);
     TapsR1 S0, S1;                                               // PF == 1: S0 = current row, S1 = next row
     issue_taps_r1(S0, R1a, R1b, w, h, gx, row_y(0), staged_flow(0, 0));
@@ -847,7 +839,7 @@ fb_iter_tma_kernel(const float* __restrict__ R, long long img_stride, const floa
         tm_wait_st();
         __syncthreads();
         // every thread is done with slot b & 1: refill it with batch b + 2
-        if (tid < 32 && b + 2 < n_batches) stage_batch(b + 2);
+        if (b + 2 < n_batches) stage_batch(b + 2);
         // ---- H phase: a warp owns row hr of the batch, a lane four adjacent outputs ---------------------------------
         const int y = r_begin + b * IT_RB + hr - IT_HALO;
         if (y >= yc0 && y < yc1) {
@@ -900,10 +892,16 @@ fb_iter_tma_kernel(const float* __restrict__ R, long long img_stride, const floa
 }
 
 template <int PF>
+__global__ void fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float* __restrict__ flow_in,
+                                  float* __restrict__ out_fwd, long long fwd_stride, float* __restrict__ out_bwd,
+                                  long long bwd_stride, int h, int w, int chunk_rows, float clampv);
+
+template <int PF, bool V3>
 static void launch_tma(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride,
                        float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, float clamp, cudaStream_t s) {
     using C = TsCfg;
-    cudaFuncSetAttribute(fb_iter_tma_kernel<PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    auto kern = V3 ? fb_iter_v3_kernel<PF> : fb_iter_tma_kernel<PF>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     const int strips = cdiv(w, C::OUT_W);
     const long long slots = 148LL * 4;
     // rows per chunk: minimise (waves of resident CTAs) x (rows a CTA marches, incl. its 12 warm-up rows)
@@ -919,11 +917,589 @@ static void launch_tma(const float* R, long long img_stride, const float* flow_i
     for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
         const int np = min(n_pairs - p0, 65535);
         dim3 g(2 * strips, chunks, np);
-        fb_iter_tma_kernel<PF><<<g, C::NT, C::SMEM_BYTES, s>>>(R + (long long)(2 * p0) * img_stride, img_stride,
+        kern<<<g, C::NT, C::SMEM_BYTES, s>>>(R + (long long)(2 * p0) * img_stride, img_stride,
                                                               flow_in + (long long)(2 * p0) * 2 * h * w,
                                                               out_fwd + p0 * fwd_stride, fwd_stride,
                                                               out_bwd + p0 * bwd_stride, bwd_stride, h, w, chunk_rows, clamp);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Packed-math kernel (the default).  The strip march is instruction-issue bound (IPC 2.3 of 4 at 16 warps per SM, DRAM
+// at 36 %: removing the whole R1 gather buys 12 %, removing the H-phase arithmetic 17 %), so this version cuts warp
+// instructions rather than bytes:
+//   * Blackwell's packed fp32 pipe (FFMA2 / FADD2 / FMUL2, one issue slot for two lanes of IEEE fp32 arithmetic):
+//     the bilinear blend works on the (c0, c1) and (c2, c3) halves of every float4 tap, the five normal-equation
+//     terms travel as two pairs + one scalar, A = (M0, M2) -> (g11, g22), B = (M3, M4) -> (h1, h2), C = M1 -> g12,
+//     through the prefix sums, the vertical window, shared memory (8-byte stores, pairs interleaved per column) and the
+//     horizontal window of the H phase.  Every operation is the same IEEE operation on the same operands in the same
+//     order as in the scalar kernel above, so the window sums are bit-identical to it;
+//   * the prefix-sum ring of the vertical window lives in tensor memory (see tm_ld5 / tm_st5);
+//   * the reciprocal of the (regularised, always normal) determinant is one MUFU.RCP (<= 1 ulp) instead of the IEEE
+//     division sequence with its slow-path branch.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef TF_RCP_EXACT
+#define TF_RCP_EXACT 0
+#endif
+typedef float2 f2;
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 dup2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ f2 lo2(float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ f2 hi2(float4 v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ f2 shfl_up2(f2 v, int d) {
+    return make_float2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
+}
+__device__ __forceinline__ f2 shfl_down2(f2 v, int d) {
+    return make_float2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+#if TF_RCP_EXACT
+    return 1.f / x;
+#else
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+
+struct PkCfg {
+    static constexpr int NT = 128, HK = 4, OUT_W = NT - 2 * IT_HALO;
+    static constexpr int ROW_FLOATS = 5 * NT;                 // [A: NT x float2][B: NT x float2][C: NT x float]
+    static constexpr int VBUF_FLOATS = 8 * ROW_FLOATS;        // 2 buffers x 4 rows
+    static constexpr int SMEM_BYTES = VBUF_FLOATS * 4;
+    static constexpr int TM_COLS = 64;
+};
+
+// FarnebackUpdateMatrices for one pixel: (A, B, C) = ((M0, M2), (M3, M4), M1)
+__device__ __forceinline__ void matrix_pk(const Taps& t, int y, int h, float sc_x, f2& mA, f2& mB, float& mC) {
+    f2 r23, r45;
+    float r6;
+    const f2 half2 = make_float2(0.5f, 0.5f), minus1 = make_float2(-1.f, -1.f);
+    if (t.inside) {
+        const float fx = t.fx, fy = t.fy;
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        const f2 w00 = dup2(a00), w01 = dup2(a01), w10 = dup2(a10), w11 = dup2(a11);
+        r23 = fma2(w11, lo2(t.p11), fma2(w10, lo2(t.p10), fma2(w01, lo2(t.p01), mul2(w00, lo2(t.p00)))));
+        r45 = fma2(w11, hi2(t.p11), fma2(w10, hi2(t.p10), fma2(w01, hi2(t.p01), mul2(w00, hi2(t.p00)))));
+        r6 = a00 * t.q00 + a01 * t.q01 + a10 * t.q10 + a11 * t.q11;
+        r45 = mul2(add2(hi2(t.c), r45), half2);
+        r6 = (t.c4 + r6) * 0.25f;
+    } else {
+        r23 = make_float2(0.f, 0.f);
+        r45 = hi2(t.c);
+        r6 = t.c4 * 0.5f;
+    }
+    r23 = mul2(fma2(r23, minus1, lo2(t.c)), half2);             // (c - r) * 0.5
+    float r2 = r23.x, r3 = r23.y, r4 = r45.x, r5 = r45.y;
+    r2 += r4 * t.dy + r6 * t.dx;
+    r3 += r6 * t.dy + r5 * t.dx;
+    if (sc_x != 1.f || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+        const float sc = sc_x * border_factor(y, h);
+        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+    }
+    mA.x = r4 * r4 + r6 * r6;
+    mC = (r4 + r5) * r6;
+    mA.y = r5 * r5 + r6 * r6;
+    mB.x = r4 * r2 + r6 * r3;
+    mB.y = r6 * r2 + r5 * r3;
+}
+
+__device__ __forceinline__ void tm_ld_abc(f2& a, f2& b, float& c, uint32_t addr) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y) : "r"(addr) : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(c) : "r"(addr + 4) : "memory");
+}
+__device__ __forceinline__ void tm_st_abc(uint32_t addr, f2 a, f2 b, float c) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(addr + 4), "f"(c) : "memory");
+}
+
+__global__ void __launch_bounds__(PkCfg::NT, 4)
+fb_iter_pk_kernel(const float* __restrict__ R, long long img_stride, const float* __restrict__ flow_in,
+                  float* __restrict__ out_fwd, long long fwd_stride, float* __restrict__ out_bwd, long long bwd_stride,
+                  int h, int w, int chunk_rows, float clampv) {
+    using C = PkCfg;
+    constexpr int NT = C::NT, HK = C::HK;
+    extern __shared__ __align__(16) float pk_vbuf[];             // [buf][row][A | B | C]
+    __shared__ uint32_t tm_addr_s;
+    const int tid = threadIdx.x;
+    const int dir = blockIdx.x & 1, strip = blockIdx.x >> 1, pair = blockIdx.z;
+    const int yc0 = blockIdx.y * chunk_rows, yc1 = min(yc0 + chunk_rows, h);
+    const int plane = h * w;
+    const float* Rp = R + (long long)(2 * pair) * img_stride;
+    const float* Rn = Rp + img_stride;
+    const float* R0 = dir ? Rn : Rp;
+    const float* R1 = dir ? Rp : Rn;
+    RPlanes RP;
+    RP.R0a = reinterpret_cast<const float4*>(R0);
+    RP.R0b = R0 + 4 * (long long)plane;
+    RP.R1a = reinterpret_cast<const float4*>(R1);
+    RP.R1b = R1 + 4 * (long long)plane;
+    const float2* fin = reinterpret_cast<const float2*>(flow_in) + (long long)(2 * pair + dir) * plane;
+    float2* fout = reinterpret_cast<float2*>(dir ? out_bwd + (long long)pair * bwd_stride
+                                                 : out_fwd + (long long)pair * fwd_stride);
+    const int x0 = strip * C::OUT_W;
+    const int gx = min(max(x0 - IT_HALO + tid, 0), w - 1);
+    const float sc_x = border_factor(gx, w);
+    const int hr = tid >> 5, cg = tid & 31;
+
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(&tm_addr_s)), "n"(C::TM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm_base = tm_addr_s + ((uint32_t)(tid >> 5) << 21);
+    const f2 zero2 = make_float2(0.f, 0.f), minus1 = make_float2(-1.f, -1.f);
+#pragma unroll
+    for (int s = 0; s < 9; ++s) tm_st_abc(tm_base + 5 * s, zero2, zero2, 0.f);
+    tm_wait_st();
+
+    // full sums of batches b-1, b-2, b-3
+    f2 B1a = zero2, B1b = zero2, B2a = zero2, B2b = zero2, B3a = zero2, B3b = zero2;
+    float B1c = 0.f, B2c = 0.f, B3c = 0.f;
+    const int r_begin = (((yc0 - IT_HALO + 8) >> 2) << 2) - 8;
+    const int n_rows = (yc1 + IT_HALO) - r_begin;
+    const int n_batches = (n_rows + IT_RB - 1) / IT_RB;
+    int rb = 0;
+    auto row_y = [&](int i) { return min(max(r_begin + i, 0), h - 1); };
+    Taps cur;
+    issue_taps(cur, RP, w, h, gx, row_y(0), ld_stream(fin + row_y(0) * w + gx));
+    float2 fq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) fq[j] = ld_stream(fin + row_y(1 + j) * w + gx);
+
+    for (int b = 0; b < n_batches; ++b) {
+        float* vbm = pk_vbuf + (b & 1) * (IT_RB * C::ROW_FLOATS);
+        f2 Pa, Pb, olda, oldb;
+        float Pc, oldc;
+#pragma unroll
+        for (int j = 0; j < IT_RB; ++j) {
+            const int i = b * IT_RB + j;
+            Taps nxt;
+            issue_taps(nxt, RP, w, h, gx, row_y(i + 1), fq[j]);
+            fq[j] = ld_stream(fin + row_y(i + 5) * w + gx);
+            f2 mA, mB;
+            float mC;
+            matrix_pk(cur, cur.y, h, sc_x, mA, mB, mC);
+            if (j == 0) { Pa = mA; Pb = mB; Pc = mC; }
+            else { Pa = add2(Pa, mA); Pb = add2(Pb, mB); Pc = Pc + mC; }
+            // rows j..3 of batch b-3 = its full sum minus its prefix P_{j-1}
+            f2 xa = B3a, xb = B3b;
+            float xc = B3c;
+            if (j > 0) { xa = fma2(olda, minus1, xa); xb = fma2(oldb, minus1, xb); xc -= oldc; }
+            const uint32_t tslot = tm_base + (uint32_t)((rb * 3 + j) * 5);
+            if (j < IT_RB - 1) tm_ld_abc(olda, oldb, oldc, tslot);
+            float* vr = vbm + j * C::ROW_FLOATS;
+            reinterpret_cast<f2*>(vr)[tid] = add2(add2(xa, B2a), add2(B1a, Pa));
+            reinterpret_cast<f2*>(vr + 2 * NT)[tid] = add2(add2(xb, B2b), add2(B1b, Pb));
+            vr[4 * NT + tid] = (xc + B2c) + (B1c + Pc);
+            if (j < IT_RB - 1) {
+                tm_wait_ld();
+                tm_st_abc(tslot, Pa, Pb, Pc);
+            }
+            cur = nxt;
+        }
+        B3a = B2a; B3b = B2b; B3c = B2c;
+        B2a = B1a; B2b = B1b; B2c = B1c;
+        B1a = Pa; B1b = Pb; B1c = Pc;
+        rb = (rb == 2) ? 0 : rb + 1;
+        tm_wait_st();
+        __syncthreads();
+        // ---- H phase: a warp owns row hr of the batch, a lane four adjacent outputs ---------------------------------
+        const int y = r_begin + b * IT_RB + hr - IT_HALO;
+        if (y >= yc0 && y < yc1) {
+            const float* vr = vbm + hr * C::ROW_FLOATS;
+            f2 gA[HK], gB[HK];
+            float gC[HK];
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+                const float4* src = reinterpret_cast<const float4*>(vr + pr * 2 * NT) + 2 * cg;
+                const float4 u = src[0], v = src[1];
+                const f2 q0 = lo2(u), q1 = hi2(u), q2 = lo2(v), q3 = hi2(v);
+                const f2 p2 = add2(q0, q1), s2 = add2(q2, q3);
+                const f2 T = add2(p2, s2), p3 = add2(p2, q2), s3 = add2(q1, s2);
+                const f2 Tm1 = shfl_up2(T, 1), Tp1 = shfl_down2(T, 1);
+                const f2 s2m2 = shfl_up2(s2, 2), s1m2 = shfl_up2(q3, 2);
+                const f2 s3m1 = shfl_up2(s3, 1), p3p1 = shfl_down2(p3, 1);
+                const f2 p1p2 = shfl_down2(q0, 2), p2p2 = shfl_down2(p2, 2);
+                const f2 U = add2(Tm1, T);
+                f2* g = pr ? gB : gA;
+                g[0] = add2(add2(s2m2, U), p3p1);
+                g[1] = add2(add2(s1m2, U), Tp1);
+                g[2] = add2(add2(U, Tp1), p1p2);
+                g[3] = add2(add2(s3m1, T), add2(Tp1, p2p2));
+            }
+            {
+                constexpr unsigned FULL = 0xffffffffu;
+                const float4 q = reinterpret_cast<const float4*>(vr + 4 * NT)[cg];
+                const float p2 = q.x + q.y, s2 = q.z + q.w;
+                const float T = p2 + s2, p3 = p2 + q.z, s3 = q.y + s2;
+                const float Tm1 = __shfl_up_sync(FULL, T, 1), Tp1 = __shfl_down_sync(FULL, T, 1);
+                const float s2m2 = __shfl_up_sync(FULL, s2, 2), s1m2 = __shfl_up_sync(FULL, q.w, 2);
+                const float s3m1 = __shfl_up_sync(FULL, s3, 1), p3p1 = __shfl_down_sync(FULL, p3, 1);
+                const float p1p2 = __shfl_down_sync(FULL, q.x, 2), p2p2 = __shfl_down_sync(FULL, p2, 2);
+                const float U = Tm1 + T;
+                gC[0] = (s2m2 + U) + p3p1;
+                gC[1] = (s1m2 + U) + Tp1;
+                gC[2] = (U + Tp1) + p1p2;
+                gC[3] = (s3m1 + T) + (Tp1 + p2p2);
+            }
+            const float reg = 1e-3f * (float)(IT_WIN * IT_WIN) * (float)(IT_WIN * IT_WIN);
+            float2 o[HK];
+#pragma unroll
+            for (int i = 0; i < HK; ++i) {
+                const float g11 = gA[i].x, g22 = gA[i].y, g12 = gC[i];
+                const float h1 = gB[i].x, h2 = gB[i].y;
+                const float idet = rcp_fast(diff_of_products(g11, g22, g12, g12) + reg);
+                float fx = diff_of_products(g11, h2, g12, h1) * idet;
+                float fy = diff_of_products(g22, h1, g12, h2) * idet;
+                if (clampv > 0.f) {
+                    fx = fminf(fmaxf(fx, -clampv), clampv);
+                    fy = fminf(fmaxf(fy, -clampv), clampv);
+                }
+                o[i] = make_float2(fx, fy);
+            }
+            const int c0 = HK * cg;
+            const int xg = x0 - IT_HALO + c0;
+            float2* dst = fout + (long long)y * w + xg;
+#pragma unroll
+            for (int i = 0; i < HK; ++i) {
+                const int cc = c0 + i;
+                if (cc >= IT_HALO && cc < NT - IT_HALO && xg + i < w) dst[i] = o[i];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_addr_s), "n"(C::TM_COLS) : "memory");
+}
+
+static void launch_pk(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride,
+                      float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, float clamp, cudaStream_t s) {
+    using C = PkCfg;
+    const int strips = cdiv(w, C::OUT_W);
+    const long long slots = 148LL * 4;
+    // rows per chunk: minimise (waves of resident CTAs) x (rows a CTA marches, incl. its 12 warm-up rows)
+    int chunks = 1;
+    long long best = -1;
+    for (int c = 1; c <= max(1, h / 16); ++c) {
+        const long long ctas = 2LL * strips * c * n_pairs;
+        const long long cost = ((ctas + slots - 1) / slots) * (cdiv(h, c) + 2 * IT_HALO);
+        if (best < 0 || cost < best) { best = cost; chunks = c; }
+    }
+    const int chunk_rows = cdiv(h, chunks);
+    chunks = cdiv(h, chunk_rows);
+    for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
+        const int np = min(n_pairs - p0, 65535);
+        dim3 g(2 * strips, chunks, np);
+        fb_iter_pk_kernel<<<g, C::NT, C::SMEM_BYTES, s>>>(R + (long long)(2 * p0) * img_stride, img_stride,
+                                                         flow_in + (long long)(2 * p0) * 2 * h * w,
+                                                         out_fwd + p0 * fwd_stride, fwd_stride,
+                                                         out_bwd + p0 * bwd_stride, bwd_stride, h, w, chunk_rows, clamp);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// v3 (the default): TMA-staged regular streams + tensor-memory prefix ring (as fb_iter_tma_kernel, which made the march
+// issue-bound: IPC 2.9, long-scoreboard 0.6 per issue) + fewer warp instructions:
+//   * packed fp32 (FFMA2 / FADD2 / FMUL2) for the bilinear blend and for the five normal-equation terms, which travel as
+//     A = (M0, M2) -> (g11, g22), B = (M3, M4) -> (h1, h2), C = M1 -> g12 through prefix sums, vertical window,
+//     shared memory (8-byte stores) and the H phase's horizontal window: same IEEE operations in the same order as the
+//     scalar kernels, so the window sums are bit-identical to theirs;
+//   * a tap set keeps its bilinear fractions and inside flag (the flow itself is re-read from the staging ring when the
+//     row is blended) instead of recomputing floor / int conversions;
+//   * one MUFU.RCP for the reciprocal of the regularised (always normal) determinant.
+// ---------------------------------------------------------------------------------------------------------------------
+struct TapsV3 {
+    float4 p00, p01, p10, p11;
+    float q00, q01, q10, q11;
+    float fx, fy;
+    bool inside;
+};
+
+__device__ __forceinline__ void issue_taps_v3(TapsV3& t, const float4* __restrict__ R1a, const float* __restrict__ R1b,
+                                              int w, int h, int x, int y, float2 f) {
+    const float px = (float)x + f.x, py = (float)y + f.y;
+    const float flx = floorf(px), fly = floorf(py);
+    const int x1 = (int)flx, y1 = (int)fly;
+    t.fx = px - flx;
+    t.fy = py - fly;
+    t.inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+    const int xc = max(min(x1, w - 2), 0), yc = max(min(y1, h - 2), 0);
+    const float4* a0 = R1a + (yc * w + xc);
+    const float4* a1 = a0 + w;
+    const float* b0 = R1b + (yc * w + xc);
+    const float* b1 = b0 + w;
+    t.p00 = __ldg(a0);
+    t.p01 = __ldg(a0 + 1);
+    t.p10 = __ldg(a1);
+    t.p11 = __ldg(a1 + 1);
+    t.q00 = __ldg(b0);
+    t.q01 = __ldg(b0 + 1);
+    t.q10 = __ldg(b1);
+    t.q11 = __ldg(b1 + 1);
+}
+
+// FarnebackUpdateMatrices for one pixel: (A, B, C) = ((M0, M2), (M3, M4), M1); c / c4 = R0 at the pixel, f = its flow
+__device__ __forceinline__ void matrix_v3(const TapsV3& t, float4 c, float c4, float2 f, int y, int h, float sc_x, f2& mA,
+                                          f2& mB, float& mC) {
+    f2 r23, r45;
+    float r6;
+    const f2 half2 = make_float2(0.5f, 0.5f), minus1 = make_float2(-1.f, -1.f);
+    if (t.inside) {
+        const float fx = t.fx, fy = t.fy;
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        const f2 w00 = dup2(a00), w01 = dup2(a01), w10 = dup2(a10), w11 = dup2(a11);
+        r23 = fma2(w11, lo2(t.p11), fma2(w10, lo2(t.p10), fma2(w01, lo2(t.p01), mul2(w00, lo2(t.p00)))));
+        r45 = fma2(w11, hi2(t.p11), fma2(w10, hi2(t.p10), fma2(w01, hi2(t.p01), mul2(w00, hi2(t.p00)))));
+        r6 = a00 * t.q00 + a01 * t.q01 + a10 * t.q10 + a11 * t.q11;
+        r45 = mul2(add2(hi2(c), r45), half2);
+        r6 = (c4 + r6) * 0.25f;
+    } else {
+        r23 = make_float2(0.f, 0.f);
+        r45 = hi2(c);
+        r6 = c4 * 0.5f;
+    }
+    r23 = mul2(fma2(r23, minus1, lo2(c)), half2);                // (c - r) * 0.5
+    float r2 = r23.x, r3 = r23.y, r4 = r45.x, r5 = r45.y;
+    r2 += r4 * f.y + r6 * f.x;
+    r3 += r6 * f.y + r5 * f.x;
+    if (sc_x != 1.f || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+        const float sc = sc_x * border_factor(y, h);
+        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+    }
+    mA.x = r4 * r4 + r6 * r6;
+    mC = (r4 + r5) * r6;
+    mA.y = r5 * r5 + r6 * r6;
+    mB.x = r4 * r2 + r6 * r3;
+    mB.y = r6 * r2 + r5 * r3;
+}
+
+template <int PF>
+__global__ void __launch_bounds__(TsCfg::NT, 4)
+fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float* __restrict__ flow_in,
+                  float* __restrict__ out_fwd, long long fwd_stride, float* __restrict__ out_bwd, long long bwd_stride,
+                  int h, int w, int chunk_rows, float clampv) {
+    using C = TsCfg;
+    constexpr int NT = C::NT, HK = C::HK, ROWF = 5 * NT;         // a row of vertical sums: [A: NT x f2][B: NT x f2][C: NT]
+    static_assert(PF == 1 || PF == 2, "rows of R1 taps in flight");
+    extern __shared__ __align__(128) unsigned char ts_smem[];
+    float* vbuf = reinterpret_cast<float*>(ts_smem + C::VBUF_OFF);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(ts_smem + C::MBAR_OFF);
+    __shared__ uint32_t tm_addr_s;
+    const int tid = threadIdx.x;
+    const int dir = blockIdx.x & 1, strip = blockIdx.x >> 1, pair = blockIdx.z;
+    const int yc0 = blockIdx.y * chunk_rows, yc1 = min(yc0 + chunk_rows, h);
+    const int plane = h * w;
+    const float* Rp = R + (long long)(2 * pair) * img_stride;
+    const float* Rn = Rp + img_stride;
+    const float* R0 = dir ? Rn : Rp;
+    const float* R1 = dir ? Rp : Rn;
+    const float4* R0a = reinterpret_cast<const float4*>(R0);
+    const float* R0b = R0 + 4 * (long long)plane;
+    const float4* R1a = reinterpret_cast<const float4*>(R1);
+    const float* R1b = R1 + 4 * (long long)plane;
+    const float2* fin = reinterpret_cast<const float2*>(flow_in) + (long long)(2 * pair + dir) * plane;
+    float2* fout = reinterpret_cast<float2*>(dir ? out_bwd + (long long)pair * bwd_stride
+                                                 : out_fwd + (long long)pair * fwd_stride);
+    const int x0 = strip * C::OUT_W;
+    const int xs = x0 - IT_HALO;
+    const int cx0 = max(xs, 0), cx1 = min(xs + NT, w), ncol = cx1 - cx0;
+    const int gx = min(max(xs + tid, 0), w - 1);
+    const int gxs = gx - cx0;
+    const float sc_x = border_factor(gx, w);
+    const int hr = tid >> 5, cg = tid & 31;
+    const unsigned skb0 = (unsigned)(reinterpret_cast<uintptr_t>(R0b) >> 2), skf0 = (unsigned)(reinterpret_cast<uintptr_t>(fin) >> 3);
+
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tm_addr_s)), "n"(C::TM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (tid == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm_base = tm_addr_s + ((uint32_t)(tid >> 5) << 21);
+    const f2 zero2 = make_float2(0.f, 0.f), minus1 = make_float2(-1.f, -1.f);
+#pragma unroll
+    for (int s = 0; s < 9; ++s) tm_st_abc(tm_base + 5 * s, zero2, zero2, 0.f);
+    tm_wait_st();
+    f2 B1a = zero2, B1b = zero2, B2a = zero2, B2b = zero2, B3a = zero2, B3b = zero2;
+    float B1c = 0.f, B2c = 0.f, B3c = 0.f;
+    const int r_begin = (((yc0 - IT_HALO + 8) >> 2) << 2) - 8;
+    const int n_rows = (yc1 + IT_HALO) - r_begin;
+    const int n_batches = (n_rows + IT_RB - 1) / IT_RB;
+    int rb = 0;
+    auto row_y = [&](int i) { return min(max(r_begin + i, 0), h - 1); };
+
+    // staging: see fb_iter_tma_kernel
+    const int swarp = tid >> 5, slane = tid & 31;
+    const uint32_t bytes_a = (uint32_t)ncol * 16u, bytes_b = (((uint32_t)ncol + 6u) & ~3u) * 4u,
+                   bytes_f = (((uint32_t)ncol + 2u) & ~1u) * 8u;
+    const uint32_t stage_tx = IT_RB * (bytes_a + bytes_b + bytes_f);
+    const char* st_base = slane == 0 ? reinterpret_cast<const char*>(R0a)
+                        : (slane == 1 ? reinterpret_cast<const char*>(R0b) : reinterpret_cast<const char*>(fin));
+    const int st_esz = slane == 0 ? 16 : (slane == 1 ? 4 : 8);
+    const uint32_t st_bytes = slane == 0 ? bytes_a : (slane == 1 ? bytes_b : bytes_f);
+    const uint32_t st_dst = smem_u32(ts_smem) + (slane == 0 ? C::A_OFF + swarp * C::A_ROW + (cx0 - xs) * 16
+                                                 : (slane == 1 ? C::B_OFF + swarp * C::B_ROW : C::F_OFF + swarp * C::F_ROW));
+    auto stage_batch = [&](int bb) {
+        const uint32_t bar = smem_u32(&mbar[bb & 1]);
+        if (slane < 3) {
+            const int y = row_y(IT_RB * bb + swarp);
+            const uintptr_t src = (reinterpret_cast<uintptr_t>(st_base) + (long long)(y * w + cx0) * st_esz) & ~(uintptr_t)15;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(st_dst + (uint32_t)(bb & 1) * C::SLOT_BYTES), "l"(src), "r"(st_bytes), "r"(bar) : "memory");
+        }
+        if (tid == 0) mbar_arrive_expect_tx(&mbar[bb & 1], stage_tx);
+    };
+    auto staged_flow = [&](int bb, int j) {
+        const int y = row_y(IT_RB * bb + j);
+        const unsigned sk = (skf0 + (unsigned)(y * w + cx0)) & 1u;
+        return reinterpret_cast<const float2*>(ts_smem + (bb & 1) * C::SLOT_BYTES + C::F_OFF + j * C::F_ROW)[sk + gxs];
+    };
+
+    stage_batch(0);
+    if (n_batches > 1) stage_batch(1);
+    mbar_wait(&mbar[0], 0u);
+    TapsV3 S0, S1;
+    issue_taps_v3(S0, R1a, R1b, w, h, gx, row_y(0), staged_flow(0, 0));
+    if (PF == 2) issue_taps_v3(S1, R1a, R1b, w, h, gx, row_y(1), staged_flow(0, 1));
+
+    for (int b = 0; b < n_batches; ++b) {
+        float* vbm = vbuf + (b & 1) * (IT_RB * ROWF);
+        const unsigned char* slot = ts_smem + (b & 1) * C::SLOT_BYTES;
+        f2 Pa, Pb, olda, oldb;
+        float Pc, oldc;
+#pragma unroll
+        for (int j = 0; j < IT_RB; ++j) {
+            const int i = b * IT_RB + j;
+            const int y_cur = row_y(i);
+            // R0 and the flow of this row from the staging ring
+            const float4 c = reinterpret_cast<const float4*>(slot + C::A_OFF + j * C::A_ROW)[gx - xs];
+            const unsigned e_cur = (unsigned)(y_cur * w + cx0);
+            const float c4 = reinterpret_cast<const float*>(slot + C::B_OFF + j * C::B_ROW)[((skb0 + e_cur) & 3u) + gxs];
+            const float2 fcur = reinterpret_cast<const float2*>(slot + C::F_OFF + j * C::F_ROW)[((skf0 + e_cur) & 1u) + gxs];
+            // the flow of row i + PF (from row 4 - PF on it lives in the next batch's slot, staged a batch ago)
+            const int jn = j + PF;
+            const int bn = b + (jn >= IT_RB ? 1 : 0);
+            if (jn == IT_RB && bn < n_batches) mbar_wait(&mbar[bn & 1], (uint32_t)((bn >> 1) & 1));
+            float2 fnext = make_float2(0.f, 0.f);
+            if (bn < n_batches) fnext = staged_flow(bn, jn & (IT_RB - 1));
+            f2 mA, mB;
+            float mC;
+            if (PF == 1) {
+                issue_taps_v3(S1, R1a, R1b, w, h, gx, row_y(i + 1), fnext);
+                matrix_v3(S0, c, c4, fcur, y_cur, h, sc_x, mA, mB, mC);
+            } else {
+                TapsV3& st = (j & 1) ? S1 : S0;
+                matrix_v3(st, c, c4, fcur, y_cur, h, sc_x, mA, mB, mC);
+                issue_taps_v3(st, R1a, R1b, w, h, gx, row_y(i + 2), fnext);
+            }
+            if (j == 0) { Pa = mA; Pb = mB; Pc = mC; }
+            else { Pa = add2(Pa, mA); Pb = add2(Pb, mB); Pc = Pc + mC; }
+            f2 xa = B3a, xb = B3b;
+            float xc = B3c;
+            if (j > 0) { xa = fma2(olda, minus1, xa); xb = fma2(oldb, minus1, xb); xc -= oldc; }
+            const uint32_t tslot = tm_base + (uint32_t)((rb * 3 + j) * 5);
+            if (j < IT_RB - 1) tm_ld_abc(olda, oldb, oldc, tslot);
+            float* vr = vbm + j * ROWF;
+            reinterpret_cast<f2*>(vr)[tid] = add2(add2(xa, B2a), add2(B1a, Pa));
+            reinterpret_cast<f2*>(vr + 2 * NT)[tid] = add2(add2(xb, B2b), add2(B1b, Pb));
+            vr[4 * NT + tid] = (xc + B2c) + (B1c + Pc);
+            if (j < IT_RB - 1) {
+                tm_wait_ld();
+                tm_st_abc(tslot, Pa, Pb, Pc);
+            }
+            if (PF == 1) S0 = S1;
+        }
+        B3a = B2a; B3b = B2b; B3c = B2c;
+        B2a = B1a; B2b = B1b; B2c = B1c;
+        B1a = Pa; B1b = Pb; B1c = Pc;
+        rb = (rb == 2) ? 0 : rb + 1;
+        tm_wait_st();
+        __syncthreads();
+        if (b + 2 < n_batches) stage_batch(b + 2);
+        // ---- H phase: a warp owns row hr of the batch, a lane four adjacent outputs ---------------------------------
+        const int y = r_begin + b * IT_RB + hr - IT_HALO;
+        if (y >= yc0 && y < yc1) {
+            const float* vr = vbm + hr * ROWF;
+            f2 gA[HK], gB[HK];
+            float gC[HK];
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+                const float4* src = reinterpret_cast<const float4*>(vr + pr * 2 * NT) + 2 * cg;
+                const float4 u = src[0], v = src[1];
+                const f2 q0 = lo2(u), q1 = hi2(u), q2 = lo2(v), q3 = hi2(v);
+                const f2 p2 = add2(q0, q1), s2 = add2(q2, q3);
+                const f2 T = add2(p2, s2), p3 = add2(p2, q2), s3 = add2(q1, s2);
+                const f2 Tm1 = shfl_up2(T, 1), Tp1 = shfl_down2(T, 1);
+                const f2 s2m2 = shfl_up2(s2, 2), s1m2 = shfl_up2(q3, 2);
+                const f2 s3m1 = shfl_up2(s3, 1), p3p1 = shfl_down2(p3, 1);
+                const f2 p1p2 = shfl_down2(q0, 2), p2p2 = shfl_down2(p2, 2);
+                const f2 U = add2(Tm1, T);
+                f2* g = pr ? gB : gA;
+                g[0] = add2(add2(s2m2, U), p3p1);
+                g[1] = add2(add2(s1m2, U), Tp1);
+                g[2] = add2(add2(U, Tp1), p1p2);
+                g[3] = add2(add2(s3m1, T), add2(Tp1, p2p2));
+            }
+            {
+                constexpr unsigned FULL = 0xffffffffu;
+                const float4 q = reinterpret_cast<const float4*>(vr + 4 * NT)[cg];
+                const float p2 = q.x + q.y, s2 = q.z + q.w;
+                const float T = p2 + s2, p3 = p2 + q.z, s3 = q.y + s2;
+                const float Tm1 = __shfl_up_sync(FULL, T, 1), Tp1 = __shfl_down_sync(FULL, T, 1);
+                const float s2m2 = __shfl_up_sync(FULL, s2, 2), s1m2 = __shfl_up_sync(FULL, q.w, 2);
+                const float s3m1 = __shfl_up_sync(FULL, s3, 1), p3p1 = __shfl_down_sync(FULL, p3, 1);
+                const float p1p2 = __shfl_down_sync(FULL, q.x, 2), p2p2 = __shfl_down_sync(FULL, p2, 2);
+                const float U = Tm1 + T;
+                gC[0] = (s2m2 + U) + p3p1;
+                gC[1] = (s1m2 + U) + Tp1;
+                gC[2] = (U + Tp1) + p1p2;
+                gC[3] = (s3m1 + T) + (Tp1 + p2p2);
+            }
+            const float reg = 1e-3f * (float)(IT_WIN * IT_WIN) * (float)(IT_WIN * IT_WIN);
+            float2 o[HK];
+#pragma unroll
+            for (int i = 0; i < HK; ++i) {
+                const float g11 = gA[i].x, g22 = gA[i].y, g12 = gC[i];
+                const float h1 = gB[i].x, h2 = gB[i].y;
+                const float idet = rcp_fast(diff_of_products(g11, g22, g12, g12) + reg);
+                float fx = diff_of_products(g11, h2, g12, h1) * idet;
+                float fy = diff_of_products(g22, h1, g12, h2) * idet;
+                if (clampv > 0.f) {
+                    fx = fminf(fmaxf(fx, -clampv), clampv);
+                    fy = fminf(fmaxf(fy, -clampv), clampv);
+                }
+                o[i] = make_float2(fx, fy);
+            }
+            const int c0 = HK * cg;
+            const int xg = xs + c0;
+            float2* dst = fout + (long long)y * w + xg;
+#pragma unroll
+            for (int i = 0; i < HK; ++i) {
+                const int cc = c0 + i;
+                if (cc >= IT_HALO && cc < NT - IT_HALO && xg + i < w) dst[i] = o[i];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_addr_s), "n"(C::TM_COLS) : "memory");
 }
 
 int launch_fb_iteration(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride,
@@ -947,9 +1523,16 @@ int launch_fb_iteration(const float* R, long long img_stride, const float* flow_
     static const char* force_tma = getenv("TF_TMA");
     const int tma = force_tma ? atoi(force_tma) : 0;
     if (tma && w >= 2 && h >= 2) {
-        if (tma == 2) launch_tma<2>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
-        else launch_tma<1>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
+        if (tma == 3) launch_tma<2, true>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
+        else if (tma == 4) launch_tma<1, true>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
+        else if (tma == 2) launch_tma<2, false>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
+        else launch_tma<1, false>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
         return check_launch("fb iteration (tma)");
+    }
+    static const char* force_pk = getenv("TF_PK");
+    if (force_pk && atoi(force_pk) != 0) {
+        launch_pk(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
+        return check_launch("fb iteration (packed)");
     }
     static const char* force_tm = getenv("TF_TMEM");
     const bool tmem = force_tm ? (atoi(force_tm) != 0) : false;
