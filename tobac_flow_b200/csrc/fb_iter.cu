@@ -1521,7 +1521,7 @@ int launch_fb_iteration(const float* R, long long img_stride, const float* flow_
     const bool hshfl = force_hs ? (atoi(force_hs) != 0) : true;
     // TMA-staged kernel: needs 16-byte-aligned float4 planes / flow rows are handled by skews; 2-px-wide levels are not
     static const char* force_tma = getenv("TF_TMA");
-    const int tma = force_tma ? atoi(force_tma) : 0;
+    const int tma = force_tma ? atoi(force_tma) : 3;      // 3 = v3 (default); 0 = the scalar strip kernels below
     if (tma && w >= 2 && h >= 2) {
         if (tma == 3) launch_tma<2, true>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
         else if (tma == 4) launch_tma<1, true>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
