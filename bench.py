@@ -38,23 +38,48 @@ METRIC = "frames/s (fwd+bwd flow + flow-convolve), GOES CONUS 1500x2500"
 UNIT = "frames/s"
 
 
+# BASELINE.json configs: (frames, H, W, how the frames map to ranks, name)
+#   "per_rank": every rank gets `frames` frames (weak scaling: the series is frames * N long)
+#   "split":    the `frames`-frame series is split over the ranks (the 144-frame full-disk day does not fit one GPU
+#               together with all three operator outputs; at N = 1 the first `single` frames are run)
+CONFIGS = {
+    "c1": dict(frames=10, H=100, W=100, mode="per_rank", name="tests/test_flow.py-style synthetic stack 10x100x100"),
+    "c2": dict(frames=288, H=1500, W=2500, mode="per_rank", name="GOES-16 ABI CONUS-shaped synthetic BT 288 frames x 1500x2500 (1 day, 5-min)"),
+    "c3": dict(frames=1440, H=500, W=500, mode="per_rank", name="ABI mesoscale-shaped 1440 frames x 500x500 (1-min cadence)"),
+    "c4": dict(frames=96, H=3712, W=3712, mode="per_rank", name="SEVIRI full-disk-shaped 96 frames x 3712x3712 (15-min)"),
+    "c5": dict(frames=144, H=5424, W=5424, mode="split", single=48, name="GOES ABI full-disk-shaped 144 frames x 5424x5424 (10-min), time-sharded"),
+}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=288, help="frames per rank (BASELINE configs[1]: 288)")
-    ap.add_argument("--height", type=int, default=1500)
-    ap.add_argument("--width", type=int, default=2500)
-    ap.add_argument("--e2e-frames", type=int, default=24)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
+                    help="BASELINE.json configs[i-1]; c2 (the metric's GOES-CONUS day) is the default")
+    ap.add_argument("--frames", type=int, default=None, help="frames per rank (overrides the config's)")
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record at N > 1")
+    ap.add_argument("--e2e-frames", type=int, default=96)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-detection", action="store_true", help="skip the detect_growth_markers extra (not the metric)")
     ap.add_argument("--detection-frames", type=int, default=48)
     ap.add_argument("--ref-workers", type=int, default=0)
-    return ap.parse_args()
+    a = ap.parse_args()
+    cfg = CONFIGS[a.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.frames is None:
+        a.frames = cfg["frames"] if cfg["mode"] == "per_rank" else (cfg["single"] if world == 1 else cfg["frames"] // world)
+    a.height = a.height or cfg["H"]
+    a.width = a.width or cfg["W"]
+    a.config_name = cfg["name"]
+    a.config_mode = cfg["mode"]
+    return a
 
 
 def level_sizes(H, W):
@@ -265,6 +290,45 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------
 # the B200 arm
 # ----------------------------------------------------------------------------------------------------------------
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def pin_to_numa(local_rank, n_local):
+    """Pin this rank's host threads to cores of its GPU's NUMA node (the end-to-end path is host-memory / PCIe bound);
+    ranks that share a core set split it.  Returns a short description for the bench line."""
+    try:
+        import torch
+        allowed = os.sched_getaffinity(0)
+        pr = torch.cuda.get_device_properties(local_rank)
+        node = -1
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        path = f"/sys/bus/pci/devices/{bus}/numa_node"
+        if os.path.exists(path):
+            node = int(open(path).read().strip())
+        local = set(allowed)
+        if node >= 0 and os.path.exists(f"/sys/devices/system/node/node{node}/cpulist"):
+            cand = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()) & allowed
+            if cand:
+                local = cand
+        cpus = sorted(local)
+        # ranks with the same candidate set take disjoint slices of it
+        share = max(1, n_local)
+        if len(cpus) >= 2 * share:
+            per = len(cpus) // share
+            cpus = cpus[local_rank % share * per:(local_rank % share + 1) * per]
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus), "allowed": len(allowed)}
+    except Exception as e:  # pragma: no cover
+        return {"numa_node": None, "error": str(e)[:80]}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -281,19 +345,27 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    affinity0 = os.sched_getaffinity(0)
+    pinned = pin_to_numa(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
 
     T, H, W = args.frames, args.height, args.width
     N = H * W
-    # ---- synthetic input, resident in HBM: this rank's day of the 288*world-frame series --------------------------
+    # ---- synthetic input, resident in HBM: this rank's frames of the (T * world)-frame series ----------------------
     base = synthetic.base_field(H, W, 1234)
-    cores = synthetic.core_table(T * world, H, W, 1234)
-    plan = synthetic.nan_plan(T * world, H, W, 1234)
     base_t = torch.as_tensor(base, device=dev)
+
+    def series(T_total):
+        return synthetic.core_table(T_total, H, W, 1234), synthetic.nan_plan(T_total, H, W, 1234)
+
+    def fill_shard(sh, T_loc, t0, T_total, cores_, plan_):
+        for i in range(T_loc):
+            sh.buf[1 + i] = synthetic.bt_frame(base_t, t0 + i, cores_, plan_, T_total)
+        sh.buf[0] = float("nan")
+        sh.buf[-1] = float("nan")
+
+    cores, plan = series(T * world)
     shard = D.Shard(torch.empty((T + 2, H, W), dtype=torch.float32, device=dev), rank, world)
-    for i in range(T):
-        shard.buf[1 + i] = synthetic.bt_frame(base_t, rank * T + i, cores, plan, T * world)
-    shard.buf[0] = float("nan")
-    shard.buf[-1] = float("nan")
+    fill_shard(shard, T, rank * T, T * world, cores, plan)
 
     fwd = torch.empty((T, H, W, 2), dtype=torch.float32, device=dev)
     bwd = torch.empty((T + 1, H, W, 2), dtype=torch.float32, device=dev)
@@ -304,12 +376,42 @@ def run_b200(args):
     s_full = np.ones((3, 3, 3))
     s_cross = np.zeros((3, 3, 3)); s_cross[1, 1, :] = s_cross[1, :, 1] = s_cross[:, 1, 1] = 1
 
-    def step():
-        fl = D.create_flow_sharded(shard, max_value=20, fwd=fwd, bwd=bwd)          # halo exchange inside
-        fl.convolve(shard, s_diff, reducer=_lib.TF_RED_DIFF, exchange=False, out=out_diff)
-        fl.convolve(shard, s_full, dtype=None, reducer=_lib.TF_RED_SOBEL, exchange=False, out=out_sobel)
-        fl.convolve(shard, s_cross, reducer=_lib.TF_RED_NONE, exchange=False, out=out_conv)
+    def run_step(sh, fwd_, bwd_, od, os_, oc):
+        fl = D.create_flow_sharded(sh, max_value=20, fwd=fwd_, bwd=bwd_)           # halo exchange inside (side stream)
+        fl.convolve(sh, s_diff, reducer=_lib.TF_RED_DIFF, exchange=False, out=od)
+        fl.convolve(sh, s_full, dtype=None, reducer=_lib.TF_RED_SOBEL, exchange=False, out=os_)
+        fl.convolve(sh, s_cross, reducer=_lib.TF_RED_NONE, exchange=False, out=oc)
         return fl
+
+    def step():
+        return run_step(shard, fwd, bwd, out_diff, out_sobel, out_conv)
+
+    def same(a, b):
+        return bool(((a == b) | (torch.isnan(a) & torch.isnan(b))).all().item())
+
+    def sharded_parity(sh, fwd_, bwd_, od, os_, oc, t0, T_loc, T_total, cores_, plan_):
+        """Every rank recomputes, unsharded and locally, the 4-frame window around each of its shard edges (the inputs
+        are synthetic, so the neighbour's frames can be generated here) and compares the flow fields and the three
+        operator results of its edge frame bit for bit with what the sharded run (NCCL halos) produced."""
+        ok = True
+        edges = []
+        if sh.has_prev and t0 >= 2 and T_loc >= 2:
+            edges.append((t0, [t0 - 2, t0 - 1, t0, t0 + 1], 2))
+        if sh.has_next and t0 + T_loc + 1 < T_total and T_loc >= 2:
+            tg = t0 + T_loc - 1
+            edges.append((tg, [tg - 1, tg, tg + 1, tg + 2], 1))
+        for tg, win, k in edges:
+            fr = torch.stack([synthetic.bt_frame(base_t, t, cores_, plan_, T_total) for t in win])
+            fl = tfb.create_flow(fr)
+            d, sb, cv = fl.diff(fr), fl.sobel(fr), fl.convolve(fr)
+            li = tg - t0
+            ok = (ok and same(fl.forward_flow_device[k], fwd_[li]) and same(fl.backward_flow_device[k], bwd_[li])
+                  and same(d[k], od[li]) and same(sb[k], os_[li]) and same(cv[:, k], oc[:, li]))
+        if world > 1:
+            t = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = bool(t.item())
+        return ok
 
     def barrier():
         if world > 1:
@@ -342,6 +444,37 @@ def run_b200(args):
     ms_per_step = elapsed_ms / args.steps
     value = T * world / (ms_per_step / 1e3)
 
+    # ---- multi-GPU evidence: the sharded result equals a local unsharded recomputation at the shard edges; the same
+    # day split over the ranks (strong scaling) ------------------------------------------------------------------------
+    parity_ok = strong = None
+    if world > 1:
+        parity_ok = sharded_parity(shard, fwd, bwd, out_diff, out_sobel, out_conv, rank * T, T, T * world, cores, plan)
+        if not args.no_strong and args.config_mode == "per_rank" and T % world == 0 and T // world >= 2:
+            Ts = T // world
+            cores_s, plan_s = series(T)
+            sh_s = D.Shard(shard.buf[:Ts + 2], rank, world)
+            fill_shard(sh_s, Ts, rank * Ts, T, cores_s, plan_s)
+            oc_s = out_conv.view(-1)[:7 * Ts * N].view(7, Ts, H, W)
+            bufs = (sh_s, fwd[:Ts], bwd[:Ts + 1], out_diff[:Ts], out_sobel[:Ts], oc_s)
+            for _ in range(max(1, args.warmup)):
+                run_step(*bufs)
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(args.steps):
+                run_step(*bufs)
+            s1.record()
+            barrier()
+            t = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            s_ms = float(t.item()) / args.steps
+            s_ok = sharded_parity(*bufs, rank * Ts, Ts, T, cores_s, plan_s)
+            strong = {"scaling": "strong", "frames": T, "frames_per_gpu": Ts, "ms_per_step": s_ms,
+                      "value": T / (s_ms / 1e3), "unit": UNIT, "sharded_parity": s_ok,
+                      "note": f"the single {T}-frame series time-sharded over {world} GPUs (NCCL p2p halos on a side stream)"}
+            # restore this rank's frames of the weak-scaling series for the end-to-end / detection extras below
+            fill_shard(shard, T, rank * T, T * world, cores, plan)
+
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
     peak, peak_src = measured_peak()
     dom = prof["fb_iter_fullres"]
@@ -361,7 +494,7 @@ def run_b200(args):
     total_kernel_ms = sum(v["ms"] for v in prof.values())
     launches = int(sum(v["launches"] for v in prof.values()))
     roofline = {
-        "bound": "hbm", "kernel": "fb_iter_strip_kernel (fused Farneback iteration) at the full-resolution level", "achieved": achieved, "peak": peak,
+        "bound": "hbm", "kernel": "fb_iter_v3_kernel (fused Farneback iteration: TMA-staged, tensor-memory ring, packed fp32) at the full-resolution level", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "bytes_per_launch": bytes_per_launch, "avg_launch_ms": dom["ms"] / max(dom["launches"], 1),
         "share_of_step_kernel_time": dom["ms"] / total_kernel_ms if total_kernel_ms else None,
@@ -398,10 +531,12 @@ def run_b200(args):
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": Te * world / dt, "unit": UNIT, "h2d_bytes_per_step": 4 * Te * N * 4,
+        e2e = {"value": Te * world / dt, "unit": UNIT, "h2d_bytes_per_step": Te * N * 4,
                "d2h_bytes_per_step": Te * N * (4 + 8 + 28), "frames_per_step": Te,
-               "note": "create_flow + diff + sobel + convolve via the numpy API; input pinned, each operator uploads "
-                       "its operand and returns a host array; flows stay on the device (Flow keeps them resident)"}
+               "note": "create_flow + diff + sobel + convolve via the numpy API; input pinned; create_flow uploads the "
+                       "frames once per step and the three operators reuse that device copy (operand cache keyed on the "
+                       "host buffer); every operator result is copied back to a host array inside the timed region; "
+                       "flows stay on the device (Flow keeps them resident)"}
 
     # ---- extra (not the metric): the device-resident growth-marker detection on this rank's first frames ---------------
     detection = None
@@ -430,6 +565,7 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
+            os.sched_setaffinity(0, affinity0)      # the CPU baseline gets every host core the process may use
             cpu = cpu_baseline_single(H, W)
         except Exception as e:  # pragma: no cover
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
@@ -439,14 +575,20 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"GOES-16 ABI CONUS-shaped synthetic BT, {T} frames x {H}x{W} per GPU "
+            "config": {"workload": f"{args.config}: {args.config_name}; {T} frames x {H}x{W} per GPU "
                                    f"({T * world} frames time-sharded over {world} GPU(s), NCCL p2p halos): fwd+bwd "
                                    "Farneback per pair + Flow.diff + Flow.sobel(linear, f64) + Flow.convolve(7-tap stack)",
-                       "frames_per_gpu": T, "height": H, "width": W, "pyramid_levels": L,
-                       "l2": "inputs (4.3 GB of frames per GPU) are far larger than the 126 MB L2; no explicit flush"},
+                       "baseline_config": args.config, "frames_per_gpu": T, "height": H, "width": W, "pyramid_levels": L,
+                       "l2": f"inputs ({T * N * 4 / 1e9:.2f} GB of frames per GPU) "
+                             + ("are far larger than the 126 MB L2; no explicit flush" if T * N * 4 > 4 * (126 << 20)
+                                else "and working set are L2-sized: see roofline note"),
+                       "host_pinning": pinned},
             "clocks": clocks, "e2e": e2e, "detection": detection, "gpu_launches": launches // max(args.steps, 1) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
         }
+        if world > 1:
+            line["sharded_parity"] = parity_ok
+            line["strong"] = strong
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

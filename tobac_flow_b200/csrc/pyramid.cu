@@ -121,37 +121,63 @@ __global__ void __launch_bounds__(256) blur_v4_kernel(const uint8_t* __restrict_
 // (accumulated in tap order), then the horizontal ones, then OpenCV's bilinear resize weights.
 __device__ __forceinline__ float u8f(unsigned v) { return __uint_as_float(0x4B000000u | v) - 8388608.f; }
 
-// full resolution: 4 adjacent outputs per thread (W % 4 == 0)
+// full resolution: 4 adjacent outputs per thread (W % 4 == 0), FR_ROWS consecutive rows per thread: the three source rows
+// of an output row slide down in registers (one 32-bit load per new row; the two neighbour bytes come from the adjacent
+// lanes' words), so a row costs one load, six byte conversions and the 18 + 12 multiply-adds of the two 3-tap passes.
+constexpr int FR_ROWS = 8;
 __global__ void __launch_bounds__(128) blur3_fullres_kernel(const uint8_t* __restrict__ q0, const uint8_t* __restrict__ q1,
                                                             float* __restrict__ out, int H, int W, float w0, float w1,
                                                             float w2) {
     const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
+    const int yb = blockIdx.y * FR_ROWS;
     const int img = blockIdx.z;
     const int W4 = W >> 2;
-    if (x4 >= W4) return;
+    const bool active = x4 < W4;
+    const int x4c = min(x4, W4 - 1);
     const uint8_t* src = ((img & 1) ? q1 : q0) + (long long)(img >> 1) * H * W;
-    const int xb = 4 * x4;
+    const int xb = 4 * x4c;
+    const int lane = threadIdx.x & 31;
+    // the bytes left / right of this thread's word: the neighbouring lanes' words, except at the warp / image edges
+    const bool left_edge = lane == 0 || x4c == 0, right_edge = lane == 31 || x4c == W4 - 1;
     const int xl = reflect101(xb - 1, W), xr = reflect101(xb + 4, W);
-    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // vertical sums at columns xb-1 .. xb+4
+    float r[3][6];                                       // converted source rows y-1, y, y+1 at columns xb-1 .. xb+4
+    auto load_row = [&](int y, float dst[6]) {
+        const uint8_t* row = src + (long long)reflect101(y, H) * W;
+        const unsigned c = __ldg(reinterpret_cast<const unsigned*>(row) + x4c);
+        const unsigned cl = __shfl_up_sync(0xffffffffu, c, 1), cr = __shfl_down_sync(0xffffffffu, c, 1);
+        dst[0] = left_edge ? u8f(__ldg(row + xl)) : byte_to_float(cl, 0x7543u);
+        dst[1] = byte_to_float(c, 0x7540u);
+        dst[2] = byte_to_float(c, 0x7541u);
+        dst[3] = byte_to_float(c, 0x7542u);
+        dst[4] = byte_to_float(c, 0x7543u);
+        dst[5] = right_edge ? u8f(__ldg(row + xr)) : byte_to_float(cr, 0x7540u);
+    };
+    load_row(yb - 1, r[0]);
+    load_row(yb, r[1]);
+    float4* dst = reinterpret_cast<float4*>(out + ((long long)img * H + yb) * W) + x4c;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const uint8_t* row = src + (long long)reflect101(y + k - 1, H) * W;
-        const unsigned c = __ldg(reinterpret_cast<const unsigned*>(row) + x4);
-        const float wk = k == 0 ? w0 : (k == 1 ? w1 : w2);
-        v[0] += wk * u8f(__ldg(row + xl));
-        v[1] += wk * byte_to_float(c, 0x7540u);
-        v[2] += wk * byte_to_float(c, 0x7541u);
-        v[3] += wk * byte_to_float(c, 0x7542u);
-        v[4] += wk * byte_to_float(c, 0x7543u);
-        v[5] += wk * u8f(__ldg(row + xr));
+    for (int i = 0; i < FR_ROWS; ++i) {
+        if (yb + i >= H) break;                          // uniform across the block
+        load_row(yb + i + 1, r[(i + 2) % 3]);
+        const float* ra = r[i % 3];
+        const float* rb = r[(i + 1) % 3];
+        const float* rc = r[(i + 2) % 3];
+        float v[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            float a = 0.f;
+            a += w0 * ra[c];
+            a += w1 * rb[c];
+            a += w2 * rc[c];
+            v[c] = a;
+        }
+        float4 o;
+        o.x = (w0 * v[0] + w1 * v[1]) + w2 * v[2];
+        o.y = (w0 * v[1] + w1 * v[2]) + w2 * v[3];
+        o.z = (w0 * v[2] + w1 * v[3]) + w2 * v[4];
+        o.w = (w0 * v[3] + w1 * v[4]) + w2 * v[5];
+        if (active) dst[(long long)i * W4] = o;
     }
-    float4 o;
-    o.x = (w0 * v[0] + w1 * v[1]) + w2 * v[2];
-    o.y = (w0 * v[1] + w1 * v[2]) + w2 * v[3];
-    o.z = (w0 * v[2] + w1 * v[3]) + w2 * v[4];
-    o.w = (w0 * v[3] + w1 * v[4]) + w2 * v[5];
-    reinterpret_cast<float4*>(out + ((long long)img * H + y) * W)[x4] = o;
 }
 
 // down-sampled level with a 3-tap blur: one output per thread from its 4 x 4 source footprint
@@ -239,8 +265,8 @@ __global__ void __launch_bounds__(256) blur3_resize_kernel(const uint8_t* __rest
 // skewed by one float per 32 columns so that the stride-`scale` reads of step 3 are bank-conflict free.
 __device__ __forceinline__ int skew32(int c) { return c + (c >> 5); }
 
-template <int TW, int TH>
-__global__ void __launch_bounds__(256) blur_resize_tile_kernel(const uint8_t* __restrict__ q0, const uint8_t* __restrict__ q1,
+template <int TW, int TH, int KS>
+__global__ void __launch_bounds__(256, 6) blur_resize_tile_kernel(const uint8_t* __restrict__ q0, const uint8_t* __restrict__ q1,
                                                                float* __restrict__ out, int H, int W, int h, int w,
                                                                double scale_x, double scale_y, int FWp, int FH,
                                                                BlurTaps taps) {
@@ -248,28 +274,41 @@ __global__ void __launch_bounds__(256) blur_resize_tile_kernel(const uint8_t* __
     const int VP = skew32(FWp) + 1;                              // pitch of a row of vertical sums
     unsigned* foot = reinterpret_cast<unsigned*>(pyr_smem);      // [FH][FWp / 4] words of 4 pixels
     float* V = reinterpret_cast<float*>(pyr_smem + (size_t)FH * FWp);   // [2 * TH][VP]
+    // resize coordinates of the tile's columns / rows (cv::resize works them out in double; once per tile, not per use)
+    __shared__ int s_x0[TW], s_y0[TH];
+    __shared__ float s_fx[TW], s_fy[TH];
+    __shared__ unsigned char s_x1[TW], s_y1[TH];                 // 1: second tap = first + 1; 0: clamped onto the first
     const int tid = threadIdx.x;
     const int img = blockIdx.z;
     const uint8_t* src = ((img & 1) ? q1 : q0) + (long long)(img >> 1) * H * W;
     const int i0 = blockIdx.x * TW, j0 = blockIdx.y * TH;
     const int ni = min(TW, w - i0), nj = min(TH, h - j0);
-    const int rad = taps.ksize >> 1;
-    int xa, ya, t0, t1; float tf;
-    resize_coord(i0, scale_x, W, xa, t1, tf);
-    resize_coord(j0, scale_y, H, ya, t1, tf);
-    xa -= rad; ya -= rad;
+    const int ksize = KS > 0 ? KS : taps.ksize;                  // KS > 0: compile-time blur width (loops fully unrolled)
+    const int rad = ksize >> 1;
+    if (tid < TW) {
+        int a, b2; float f;
+        resize_coord(min(i0 + tid, w - 1), scale_x, W, a, b2, f);
+        s_x0[tid] = a; s_x1[tid] = (unsigned char)(b2 - a); s_fx[tid] = f;
+    } else if (tid >= 128 && tid < 128 + TH) {
+        int a, b2; float f;
+        resize_coord(min(j0 + tid - 128, h - 1), scale_y, H, a, b2, f);
+        s_y0[tid - 128] = a; s_y1[tid - 128] = (unsigned char)(b2 - a); s_fy[tid - 128] = f;
+    }
+    __syncthreads();
+    const int xa = s_x0[0] - rad, ya = s_y0[0] - rad;
     const int xal = xa & ~3;                                     // footprint starts at a 4-pixel boundary (may be < 0)
-    resize_coord(i0 + ni - 1, scale_x, W, t0, t1, tf);
-    const int fw4 = min((t1 + rad - xal) / 4 + 1, FWp / 4);      // words per footprint row actually needed
-    resize_coord(j0 + nj - 1, scale_y, H, t0, t1, tf);
-    const int fh = min(t1 + rad - ya + 1, FH);
+    const int fw4 = min((s_x0[ni - 1] + s_x1[ni - 1] + rad - xal) / 4 + 1, FWp / 4);   // words per footprint row in use
+    const int fh = min(s_y0[nj - 1] + s_y1[nj - 1] + rad - ya + 1, FH);
     const int W4 = FWp >> 2;
+    const float inv_fw4 = 1.f / (float)fw4;                      // idx / fw4 == (int)((idx + 0.5f) * inv_fw4) for idx < 2^20
 
-    // 1. footprint
+    // 1. footprint (measured: a warp per row with 16-byte loads is slower -- the wider, 16-aligned footprint costs a CTA
+    // per SM at the deep levels)
     const bool rows_aligned = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0;
     for (int idx = tid; idx < fh * fw4; idx += 256) {
-        const int r = idx / fw4, c4 = idx - r * fw4;
-        const int gy = reflect101(ya + r, H);
+        const int r = (int)(((float)idx + 0.5f) * inv_fw4), c4 = idx - r * fw4;
+        int gy = ya + r;
+        if ((unsigned)gy >= (unsigned)H) gy = reflect101(gy, H);
         const int gx = xal + 4 * c4;
         const uint8_t* row = src + (long long)gy * W;
         unsigned v;
@@ -286,17 +325,15 @@ __global__ void __launch_bounds__(256) blur_resize_tile_kernel(const uint8_t* __
 
     // 2. vertical blur: task = (destination row, 4 columns)
     for (int idx = tid; idx < nj * fw4; idx += 256) {
-        const int j = idx / fw4, c4 = idx - j * fw4;
-        int y0, y1; float fy;
-        resize_coord(j0 + j, scale_y, H, y0, y1, fy);
-        const unsigned* p = foot + (y0 - rad - ya) * W4 + c4;
+        const int j = (int)(((float)idx + 0.5f) * inv_fw4), c4 = idx - j * fw4;
+        const unsigned* p = foot + (s_y0[j] - rad - ya) * W4 + c4;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-        if (y1 == y0 + 1) {
+        if (s_y1[j]) {
             float wprev = 0.f;
-#pragma unroll 4
-            for (int k = 0; k <= taps.ksize; ++k) {
+#pragma unroll (KS > 0 ? KS + 1 : 4)
+            for (int k = 0; k <= ksize; ++k) {
                 const unsigned c = p[k * W4];
-                const float wk = k < taps.ksize ? taps.w[k] : 0.f;
+                const float wk = k < ksize ? taps.w[k] : 0.f;
                 const float v0 = byte_to_float(c, 0x7540u), v1 = byte_to_float(c, 0x7541u);
                 const float v2 = byte_to_float(c, 0x7542u), v3 = byte_to_float(c, 0x7543u);
                 a0.x += wk * v0; a0.y += wk * v1; a0.z += wk * v2; a0.w += wk * v3;
@@ -304,8 +341,8 @@ __global__ void __launch_bounds__(256) blur_resize_tile_kernel(const uint8_t* __
                 wprev = wk;
             }
         } else {
-#pragma unroll 4
-            for (int k = 0; k < taps.ksize; ++k) {
+#pragma unroll (KS > 0 ? KS + 1 : 4)
+            for (int k = 0; k < ksize; ++k) {
                 const unsigned c = p[k * W4];
                 const float wk = taps.w[k];
                 a0.x += wk * byte_to_float(c, 0x7540u);
@@ -326,17 +363,15 @@ __global__ void __launch_bounds__(256) blur_resize_tile_kernel(const uint8_t* __
     for (int idx = tid; idx < nj * TW; idx += 256) {
         const int j = idx / TW, ii = idx - j * TW;
         if (ii >= ni) continue;
-        int x0, x1, y0, y1; float fx, fy;
-        resize_coord(i0 + ii, scale_x, W, x0, x1, fx);
-        resize_coord(j0 + j, scale_y, H, y0, y1, fy);
+        const float fx = s_fx[ii], fy = s_fy[j];
         const float* row0 = V + (2 * j) * VP;
         const float* row1 = row0 + VP;
-        const int c0 = x0 - rad - xal;
+        const int c0 = s_x0[ii] - rad - xal;
         float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
-        if (x1 == x0 + 1) {
+        if (s_x1[ii]) {
             float a0 = row0[skew32(c0)], a1 = row1[skew32(c0)];
-#pragma unroll 4
-            for (int k = 0; k < taps.ksize; ++k) {
+#pragma unroll (KS > 0 ? KS + 1 : 4)
+            for (int k = 0; k < ksize; ++k) {
                 const float wk = taps.w[k];
                 const int cs = skew32(c0 + k + 1);
                 const float n0 = row0[cs], n1 = row1[cs];
@@ -348,7 +383,7 @@ __global__ void __launch_bounds__(256) blur_resize_tile_kernel(const uint8_t* __
                 a1 = n1;
             }
         } else {
-            for (int k = 0; k < taps.ksize; ++k) {
+            for (int k = 0; k < ksize; ++k) {
                 const float wk = taps.w[k];
                 const int cs = skew32(c0 + k);
                 b00 += wk * row0[cs];
@@ -518,8 +553,9 @@ int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int 
         const int n_launch = cdiv(n_img, 65534);
         LaunchTimer lt(KC_PYRAMID, (2.0 * H * W + 8.0 * h * w) * n_pairs, s, n_launch);
         const bool wide = sx < 3.0;                              // half resolution: 64 x 16 tiles, else 32 x 8 / 16 x 8 / 8 x 4
+        // (deep levels: few rows per tile, so that the footprint leaves room for 5-6 CTAs per SM)
         const int TW = wide ? 64 : (sx < 6.0 ? 32 : (sx < 24.0 ? 16 : 8));
-        const int TH = wide ? 16 : (sx < 24.0 ? 8 : 4);
+        const int TH = wide ? 16 : (sx < 12.0 ? 8 : (sx < 24.0 ? 4 : 2));
         const int FWp = (((int)ceil((TW - 1) * sx) + 2 + ksize + 3 + 3) / 4 + 1) * 4;   // + alignment slack
         const int FH = (int)ceil((TH - 1) * sy) + 3 + ksize;
         const size_t smem = (size_t)FH * FWp + (size_t)2 * TH * (FWp + FWp / 32 + 2) * sizeof(float);
@@ -530,15 +566,18 @@ int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int 
                 const uint8_t* a1 = q1 + (long long)(z0 / 2) * H * W;
                 float* oz = out + (long long)z0 * h * w;
                 dim3 g(cdiv(w, TW), cdiv(h, TH), nz);
-#define TF_TILE_LAUNCH(TW_, TH_)                                                                                       \
+#define TF_TILE_LAUNCH(TW_, TH_, KS_)                                                                                  \
     do {                                                                                                               \
-        cudaFuncSetAttribute(blur_resize_tile_kernel<TW_, TH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        blur_resize_tile_kernel<TW_, TH_><<<g, 256, smem, s>>>(a0, a1, oz, H, W, h, w, sx, sy, FWp, FH, taps);         \
+        cudaFuncSetAttribute(blur_resize_tile_kernel<TW_, TH_, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        blur_resize_tile_kernel<TW_, TH_, KS_><<<g, 256, smem, s>>>(a0, a1, oz, H, W, h, w, sx, sy, FWp, FH, taps);   \
     } while (0)
-                if (TW == 64) TF_TILE_LAUNCH(64, 16);
-                else if (TW == 32) TF_TILE_LAUNCH(32, 8);
-                else if (TW == 16) TF_TILE_LAUNCH(16, 8);
-                else TF_TILE_LAUNCH(8, 4);
+                if (TW == 64 && ksize == 3) TF_TILE_LAUNCH(64, 16, 3);
+                else if (TW == 64) TF_TILE_LAUNCH(64, 16, 0);
+                else if (TW == 32 && ksize == 9) TF_TILE_LAUNCH(32, 8, 9);
+                else if (TW == 32) TF_TILE_LAUNCH(32, 8, 0);
+                else if (TW == 16 && TH == 8) TF_TILE_LAUNCH(16, 8, 0);
+                else if (TW == 16) TF_TILE_LAUNCH(16, 4, 0);
+                else TF_TILE_LAUNCH(8, 2, 0);
 #undef TF_TILE_LAUNCH
             }
             return check_launch("pyramid level (tile)");
@@ -554,7 +593,7 @@ int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int 
         if (fused3) {
             float* o3 = out + (long long)z0 * h * w;
             if (h == H && w == W && W % 4 == 0 && (((uintptr_t)a0 | (uintptr_t)a1) % 4 == 0) && (uintptr_t)o3 % 16 == 0) {
-                dim3 g(cdiv(W / 4, 128), H, nz);
+                dim3 g(cdiv(W / 4, 128), cdiv(H, FR_ROWS), nz);
                 blur3_fullres_kernel<<<g, 128, 0, s>>>(a0, a1, o3, H, W, taps.w[0], taps.w[1], taps.w[2]);
                 continue;
             }

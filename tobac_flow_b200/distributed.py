@@ -109,6 +109,16 @@ class CudaOps:
         return h[0], h[1], h[2], h[3]
 
 
+_HALO_STREAMS = {}
+
+
+def _halo_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _HALO_STREAMS:
+        _HALO_STREAMS[key] = torch.cuda.Stream(dev)
+    return _HALO_STREAMS[key]
+
+
 def _p2p(ops, group):
     if ops:
         for w in dist.batch_isend_irecv(ops):
@@ -267,8 +277,6 @@ def create_flow_sharded(shard: Shard, smoothing_passes=0, interp_method="linear"
     """``create_flow`` for one rank of a time-sharded series; ``shard.buf[1:-1]`` holds the rank's frames."""
     ops = ops or CudaOps()
     rank, world = shard.rank, shard.world
-    if exchange:
-        shard.exchange_halos(group)
     T_loc, H, W = shard.local.shape
     dev = shard.buf.device
     if fwd is None:
@@ -276,11 +284,35 @@ def create_flow_sharded(shard: Shard, smoothing_passes=0, interp_method="linear"
     if bwd is None:
         # one extra slot: backward_flow of the next rank's first frame, produced here, sent on below
         bwd = torch.full((T_loc + 1, H, W, 2), float("nan"), dtype=torch.float32, device=dev)
-    frames = shard.buf[1:T_loc + 2] if shard.has_next else shard.buf[1:T_loc + 1]
-    if vr_steps:
-        ops.calculate_flow(frames, fwd, bwd, smoothing_passes, interp_method, max_value, vr_steps=vr_steps)
     else:
-        ops.calculate_flow(frames, fwd, bwd, smoothing_passes, interp_method, max_value)
+        assert fwd.dtype == torch.float32 and bwd.dtype == torch.float32 and fwd.is_contiguous() and bwd.is_contiguous()
+        assert tuple(fwd.shape) == (T_loc, H, W, 2) and tuple(bwd.shape) == (T_loc + 1, H, W, 2), "fwd (T_loc,..) / bwd (T_loc+1,..)"
+    kw = dict(vr_steps=vr_steps) if vr_steps else {}
+    halo_ready = None
+    if exchange and world > 1 and dev.type == "cuda":
+        # the one-frame halos travel on a side stream (NCCL p2p over NVLink) while the interior pairs, which only read
+        # this rank's own frames, are computed; the stream rejoins before the boundary pair (T_loc - 1, T_loc)
+        cur = torch.cuda.current_stream(dev)
+        side = _halo_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            shard.exchange_halos(group)
+            halo_ready = torch.cuda.Event()
+            halo_ready.record(side)
+        shard.buf.record_stream(side)
+    elif exchange:
+        shard.exchange_halos(group)
+    if halo_ready is not None and T_loc >= 2:
+        ops.calculate_flow(shard.buf[1:T_loc + 1], fwd, bwd, smoothing_passes, interp_method, max_value, **kw)
+        torch.cuda.current_stream(dev).wait_event(halo_ready)
+        if shard.has_next:
+            ops.calculate_flow(shard.buf[T_loc:T_loc + 2], fwd[T_loc - 1:], bwd[T_loc - 1:], smoothing_passes,
+                               interp_method, max_value, **kw)
+    else:
+        if halo_ready is not None:
+            torch.cuda.current_stream(dev).wait_event(halo_ready)
+        frames = shard.buf[1:T_loc + 2] if shard.has_next else shard.buf[1:T_loc + 1]
+        ops.calculate_flow(frames, fwd, bwd, smoothing_passes, interp_method, max_value, **kw)
     if world > 1:
         p2p = []
         if shard.has_next:

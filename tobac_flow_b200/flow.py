@@ -107,6 +107,102 @@ def _side_streams(dev):
     return _SIDE_STREAMS[key]
 
 
+class _OperandCache:
+    """Device copies of host operands, so that ``create_flow(bt)`` followed by ``flow.diff(bt)``, ``flow.sobel(bt)``,
+    ``flow.convolve(bt)`` uploads ``bt`` once instead of four times.
+
+    Key = (buffer address, shape, strides, dtype) of the host array.  Guards against stale hits: the entry dies with the
+    array object it was made from (weak reference), and a fingerprint of ~4 k sampled elements plus both ends of the
+    buffer is re-taken on every lookup, so an array that was modified in place is uploaded again (a write that misses
+    every sampled element is not detected: ``TF_OPERAND_CACHE=0`` or :func:`operand_cache_clear` switch the cache off /
+    empty it).  Bounded by ``TF_OPERAND_CACHE_MB`` (default 16 GiB, at most a quarter of the device memory), LRU.
+    """
+
+    def __init__(self):
+        self.entries = {}          # key -> [tensor, fingerprint, weakref, bytes]
+        self.order = []
+        self.bytes = 0
+
+    @staticmethod
+    def enabled():
+        return os.environ.get("TF_OPERAND_CACHE", "1") != "0"
+
+    @staticmethod
+    def _key(a: np.ndarray):
+        return (a.__array_interface__["data"][0], a.shape, a.strides, a.dtype.str)
+
+    @staticmethod
+    def _fingerprint(a: np.ndarray):
+        flat = a.reshape(-1)
+        n = flat.shape[0]
+        if n == 0:
+            return 0
+        step = max(1, n // 4096)
+        sample = np.concatenate([flat[::step], flat[:64], flat[-64:]])
+        return hash(sample.tobytes())
+
+    def _limit(self):
+        mb = os.environ.get("TF_OPERAND_CACHE_MB")
+        if mb is not None:
+            return int(mb) << 20
+        total = torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
+        return min(16 << 30, total // 4)
+
+    def _drop(self, key):
+        e = self.entries.pop(key, None)
+        if e is not None:
+            self.bytes -= e[3]
+            if key in self.order:
+                self.order.remove(key)
+
+    def get(self, a: np.ndarray, dev):
+        if not self.enabled() or not a.flags.c_contiguous:
+            return None
+        key = self._key(a)
+        e = self.entries.get(key)
+        if e is None:
+            return None
+        if e[2]() is None or e[0].device != dev or e[1] != self._fingerprint(a):
+            self._drop(key)
+            return None
+        self.order.remove(key)
+        self.order.append(key)
+        return e[0]
+
+    def put(self, a: np.ndarray, t: torch.Tensor):
+        if not self.enabled() or not a.flags.c_contiguous:
+            return
+        import weakref
+        nbytes = t.numel() * t.element_size()
+        limit = self._limit()
+        if nbytes > limit:
+            return
+        key = self._key(a)
+        self._drop(key)
+        while self.order and self.bytes + nbytes > limit:
+            self._drop(self.order[0])
+        try:
+            ref = weakref.ref(a, lambda _r, k=key: self._drop(k))
+        except TypeError:
+            return
+        self.entries[key] = [t, self._fingerprint(a), ref, nbytes]
+        self.order.append(key)
+        self.bytes += nbytes
+
+    def clear(self):
+        self.entries.clear()
+        self.order.clear()
+        self.bytes = 0
+
+
+_OPERANDS = _OperandCache()
+
+
+def operand_cache_clear():
+    """Forget every cached device copy of a host operand (see ``_OperandCache``)."""
+    _OPERANDS.clear()
+
+
 def _dtype_code(np_dtype):
     """``dtype=`` of the reference (a numpy dtype or None -> float64, np.full semantics) -> (torch dtype, code)."""
     dt = np.dtype(np.float64 if np_dtype is None else np_dtype)
@@ -345,6 +441,7 @@ class Flow:
             a = a.astype(np.float32)
         elif a.dtype not in (np.float32, np.float64, np.int32):
             raise NotImplementedError(f"operand dtype {a.dtype} is not supported")
+        resident = _OPERANDS.get(a, dev)       # the device copy a previous create_flow / operator call left behind
         src = torch.from_numpy(a)
         T, H, W = src.shape
         out_t, _ = _dtype_code(dtype)
@@ -362,19 +459,23 @@ class Flow:
         s_in, s_out = _side_streams(dev)
         # the operand buffer belongs to the upload stream's pool, so the copies need not wait for the work already queued
         # on the current stream (typically the flow kernels of the create_flow call just before): they run underneath it
-        with torch.cuda.stream(s_in):
-            d_in = torch.empty((T, H, W), dtype=src.dtype, device=dev)
-        d_in.record_stream(cur)
         s_out.wait_stream(cur)
         ev_in = []
-        with torch.cuda.stream(s_in):
-            for a0, b0 in chunks:
-                d_in[a0:b0].copy_(src[a0:b0], non_blocking=True)
-                ev_in.append(torch.cuda.Event())
-                ev_in[-1].record(s_in)
+        if resident is not None:
+            d_in = resident
+        else:
+            with torch.cuda.stream(s_in):
+                d_in = torch.empty((T, H, W), dtype=src.dtype, device=dev)
+            d_in.record_stream(cur)
+            with torch.cuda.stream(s_in):
+                for a0, b0 in chunks:
+                    d_in[a0:b0].copy_(src[a0:b0], non_blocking=True)
+                    ev_in.append(torch.cuda.Event())
+                    ev_in[-1].record(s_in)
         bufs, ev_free = [None, None], [None, None]
         for k, (a0, b0) in enumerate(chunks):
-            cur.wait_event(ev_in[min(k + 1, len(chunks) - 1)])      # this chunk and its right halo frame are here
+            if ev_in:
+                cur.wait_event(ev_in[min(k + 1, len(chunks) - 1)])  # this chunk and its right halo frame are here
             slot = k & 1
             if ev_free[slot] is not None:
                 cur.wait_event(ev_free[slot])                       # the buffer's previous contents are on the host
@@ -397,6 +498,8 @@ class Flow:
                 ev_free[slot].record(s_out)
         s_out.synchronize()
         cur.wait_stream(s_in)
+        if resident is None:
+            _OPERANDS.put(a, d_in)
         return host.numpy()
 
     def _convolve_python_func(self, t, structure, method, fill_value, dtype, func):
@@ -520,6 +623,8 @@ def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Te
     fuse_clamp = (max_value is not None) and smoothing_passes == 0 and not use_vr
     params = _lib.default_params(max_value if fuse_clamp else 0.0)
     nb = batch or _pair_batch(n_pairs, H, W, params, use_vr)
+    # (measured: alternating consecutive pair batches between two streams, to fill the half-empty grids of the small
+    # pyramid levels and the tail waves, gains nothing: 458-475 vs 460 ms per CONUS day)
     dev = frames.device
     q0 = torch.empty((nb, H, W), dtype=torch.uint8, device=dev)
     q1 = torch.empty((nb, H, W), dtype=torch.uint8, device=dev)
@@ -603,6 +708,8 @@ def _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_meth
         def frames_ready(last_frame):
             torch.cuda.current_stream().wait_event(events[min(last_frame // _HOST_PAIR_BATCH, len(events) - 1)])
         batch = _HOST_PAIR_BATCH
+        frames.record_stream(s_in)
+        _OPERANDS.put(host_a if host_a.flags.c_contiguous else src.numpy(), frames)   # the operators reuse this copy
     else:
         frames, _ = _to_device(data)
         if frames.dtype not in (torch.float32, torch.float64):
