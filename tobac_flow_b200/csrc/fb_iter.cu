@@ -891,7 +891,7 @@ fb_iter_tma_kernel(const float* __restrict__ R, long long img_stride, const floa
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_addr_s), "n"(C::TM_COLS) : "memory");
 }
 
-template <int PF>
+template <int PF, int WAL>
 __global__ void fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float* __restrict__ flow_in,
                                   float* __restrict__ out_fwd, long long fwd_stride, float* __restrict__ out_bwd,
                                   long long bwd_stride, int h, int w, int chunk_rows, float clampv);
@@ -900,7 +900,8 @@ template <int PF, bool V3>
 static void launch_tma(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride,
                        float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, float clamp, cudaStream_t s) {
     using C = TsCfg;
-    auto kern = V3 ? fb_iter_v3_kernel<PF> : fb_iter_tma_kernel<PF>;
+    auto kern = V3 ? ((w & 3) == 0 ? fb_iter_v3_kernel<PF, 2> : ((w & 1) == 0 ? fb_iter_v3_kernel<PF, 1> : fb_iter_v3_kernel<PF, 0>))
+                   : fb_iter_tma_kernel<PF>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     const int strips = cdiv(w, C::OUT_W);
     const long long slots = 148LL * 4;
@@ -1232,19 +1233,21 @@ __device__ __forceinline__ void issue_taps_v3(TapsV3& t, const float4* __restric
     t.fx = px - flx;
     t.fy = py - fly;
     t.inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
-    const int xc = max(min(x1, w - 2), 0), yc = max(min(y1, h - 2), 0);
-    const float4* a0 = R1a + (yc * w + xc);
-    const float4* a1 = a0 + w;
-    const float* b0 = R1b + (yc * w + xc);
-    const float* b1 = b0 + w;
-    t.p00 = __ldg(a0);
-    t.p01 = __ldg(a0 + 1);
-    t.p10 = __ldg(a1);
-    t.p11 = __ldg(a1 + 1);
-    t.q00 = __ldg(b0);
-    t.q01 = __ldg(b0 + 1);
-    t.q10 = __ldg(b1);
-    t.q11 = __ldg(b1 + 1);
+    // the taps of a position outside the image are never used: predicated loads instead of clamped addresses
+    if (t.inside) {
+        const float4* a0 = R1a + (y1 * w + x1);
+        const float4* a1 = a0 + w;
+        const float* b0 = R1b + (y1 * w + x1);
+        const float* b1 = b0 + w;
+        t.p00 = __ldg(a0);
+        t.p01 = __ldg(a0 + 1);
+        t.p10 = __ldg(a1);
+        t.p11 = __ldg(a1 + 1);
+        t.q00 = __ldg(b0);
+        t.q01 = __ldg(b0 + 1);
+        t.q10 = __ldg(b1);
+        t.q11 = __ldg(b1 + 1);
+    }
 }
 
 // FarnebackUpdateMatrices for one pixel: (A, B, C) = ((M0, M2), (M3, M4), M1); c / c4 = R0 at the pixel, f = its flow
@@ -1282,7 +1285,10 @@ __device__ __forceinline__ void matrix_v3(const TapsV3& t, float4 c, float c4, f
     mB.y = r6 * r2 + r5 * r3;
 }
 
-template <int PF>
+// WAL = 2: w % 4 == 0 -- every row of the 4-byte / 8-byte streams then starts at the same offset from a 16-byte
+// boundary, so the alignment skews of the staged rows are constants of the strip (hoisted) and the outputs can go out as
+// 16-byte stores.  WAL = 1: w even -- the same for the 8-byte streams (flow in, flow out) only.  WAL = 0: any w.
+template <int PF, int WAL>
 __global__ void __launch_bounds__(TsCfg::NT, 4)
 fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float* __restrict__ flow_in,
                   float* __restrict__ out_fwd, long long fwd_stride, float* __restrict__ out_bwd, long long bwd_stride,
@@ -1365,9 +1371,10 @@ fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float
         }
         if (tid == 0) mbar_arrive_expect_tx(&mbar[bb & 1], stage_tx);
     };
+    const unsigned skb_c = (skb0 + (unsigned)cx0) & 3u, skf_c = (skf0 + (unsigned)cx0) & 1u;   // WA: the skews of every row
     auto staged_flow = [&](int bb, int j) {
-        const int y = row_y(IT_RB * bb + j);
-        const unsigned sk = (skf0 + (unsigned)(y * w + cx0)) & 1u;
+        unsigned sk = skf_c;
+        if (WAL == 0) sk = (skf0 + (unsigned)(row_y(IT_RB * bb + j) * w + cx0)) & 1u;
         return reinterpret_cast<const float2*>(ts_smem + (bb & 1) * C::SLOT_BYTES + C::F_OFF + j * C::F_ROW)[sk + gxs];
     };
 
@@ -1389,9 +1396,14 @@ fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float
             const int y_cur = row_y(i);
             // R0 and the flow of this row from the staging ring
             const float4 c = reinterpret_cast<const float4*>(slot + C::A_OFF + j * C::A_ROW)[gx - xs];
-            const unsigned e_cur = (unsigned)(y_cur * w + cx0);
-            const float c4 = reinterpret_cast<const float*>(slot + C::B_OFF + j * C::B_ROW)[((skb0 + e_cur) & 3u) + gxs];
-            const float2 fcur = reinterpret_cast<const float2*>(slot + C::F_OFF + j * C::F_ROW)[((skf0 + e_cur) & 1u) + gxs];
+            unsigned skb = skb_c, skf = skf_c;
+            if (WAL < 2) {
+                const unsigned e_cur = (unsigned)(y_cur * w + cx0);
+                skb = (skb0 + e_cur) & 3u;
+                if (WAL == 0) skf = (skf0 + e_cur) & 1u;
+            }
+            const float c4 = reinterpret_cast<const float*>(slot + C::B_OFF + j * C::B_ROW)[skb + gxs];
+            const float2 fcur = reinterpret_cast<const float2*>(slot + C::F_OFF + j * C::F_ROW)[skf + gxs];
             // the flow of row i + PF (from row 4 - PF on it lives in the next batch's slot, staged a batch ago)
             const int jn = j + PF;
             const int bn = b + (jn >= IT_RB ? 1 : 0);
@@ -1489,10 +1501,20 @@ fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float
             const int c0 = HK * cg;
             const int xg = xs + c0;
             float2* dst = fout + (long long)y * w + xg;
+            if (WAL >= 1 && (reinterpret_cast<uintptr_t>(fout) & 15) == 0) {
+                // xg and w are even: the output pairs (0, 1) and (2, 3) are 16-byte aligned and valid / invalid together
 #pragma unroll
-            for (int i = 0; i < HK; ++i) {
-                const int cc = c0 + i;
-                if (cc >= IT_HALO && cc < NT - IT_HALO && xg + i < w) dst[i] = o[i];
+                for (int i = 0; i < HK; i += 2) {
+                    const int cc = c0 + i;
+                    if (cc >= IT_HALO && cc < NT - IT_HALO && xg + i < w)
+                        *reinterpret_cast<float4*>(dst + i) = make_float4(o[i].x, o[i].y, o[i + 1].x, o[i + 1].y);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < HK; ++i) {
+                    const int cc = c0 + i;
+                    if (cc >= IT_HALO && cc < NT - IT_HALO && xg + i < w) dst[i] = o[i];
+                }
             }
         }
     }
