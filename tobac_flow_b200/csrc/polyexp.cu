@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256) polyexp_kernel(const float* __restrict__ 
     float4* dst_a = reinterpret_cast<float4*>(R + (long long)img * img_stride);
     float* dst_b = R + (long long)img * img_stride + 4 * (long long)plane;
     constexpr int GROUPS = PE_SW / 4 - 2;     // 30 groups of 4 output columns (the last one is partly beyond PE_TW)
+    const bool wide_ok = (w & 1) == 0 && (reinterpret_cast<uintptr_t>(dst_a) & 31) == 0;   // 32-byte aligned texel pairs
     for (int task = tid; task < PE_TH * GROUPS; task += 256) {
         const int r = task / GROUPS, cgp = task - r * GROUPS;
         const int c0 = 4 * cgp;               // first output column (tile-relative); its region column is c0 + PE_N
@@ -89,10 +90,10 @@ __global__ void __launch_bounds__(256) polyexp_kernel(const float* __restrict__ 
             v1[4 * q] = b.x; v1[4 * q + 1] = b.y; v1[4 * q + 2] = b.z; v1[4 * q + 3] = b.w;
             v2[4 * q] = d.x; v2[4 * q + 1] = d.y; v2[4 * q + 2] = d.z; v2[4 * q + 3] = d.w;
         }
+        float4 oa[4];
+        float ob[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int gx = x0 + c0 + i;
-            if (c0 + i >= PE_TW || gx >= w) continue;
             const int m = i + PE_N;           // index of the output's own column in v*
             float b1 = v0[m] * pc.g[0], b2 = 0.f, b3 = v1[m] * pc.g[0], b4 = 0.f, b5 = v2[m] * pc.g[0], b6 = 0.f;
 #pragma unroll
@@ -105,20 +106,47 @@ __global__ void __launch_bounds__(256) polyexp_kernel(const float* __restrict__ 
                 b6 += (v1[m + k] - v1[m - k]) * pc.xg[k];
                 b5 += (v2[m + k] + v2[m - k]) * pc.g[k];
             }
-            const int o = gy * w + gx;
-            dst_a[o] = make_float4(b3 * pc.ig11, b2 * pc.ig11, b1 * pc.ig03 + b5 * pc.ig33, b1 * pc.ig03 + b4 * pc.ig33);
-            dst_b[o] = b6 * pc.ig55;
+            oa[i] = make_float4(b3 * pc.ig11, b2 * pc.ig11, b1 * pc.ig03 + b5 * pc.ig33, b1 * pc.ig03 + b4 * pc.ig33);
+            ob[i] = b6 * pc.ig55;
+        }
+        // A thread's four texels are 64 contiguous bytes of the float4 plane.  Lanes are 64 bytes apart, so four 16-byte
+        // stores touch every 128-byte line of the warp's 2 KB span four times; Blackwell's 256-bit stores (STG.256) halve
+        // that.  Tile width and group offset are even, so with an even w the pairs (0, 1) and (2, 3) are 32-byte aligned
+        // and inside / outside the image together.
+        const int gx0 = x0 + c0;
+        const long long o = (long long)gy * w + gx0;
+        const int nvalid = max(0, min(4, min(PE_TW - c0, w - gx0)));
+        if (wide_ok && (nvalid & 1) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i += 2) {
+                if (i >= nvalid) break;
+                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                             ::"l"(dst_a + o + i), "f"(oa[i].x), "f"(oa[i].y), "f"(oa[i].z), "f"(oa[i].w), "f"(oa[i + 1].x),
+                               "f"(oa[i + 1].y), "f"(oa[i + 1].z), "f"(oa[i + 1].w) : "memory");
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i < nvalid) dst_a[o + i] = oa[i];
+        }
+        if (nvalid == 4 && ((reinterpret_cast<uintptr_t>(dst_b + o)) & 15) == 0) {
+            *reinterpret_cast<float4*>(dst_b + o) = make_float4(ob[0], ob[1], ob[2], ob[3]);
+        } else if ((nvalid & 1) == 0 && ((reinterpret_cast<uintptr_t>(dst_b + o)) & 7) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i += 2)
+                if (i < nvalid) *reinterpret_cast<float2*>(dst_b + o + i) = make_float2(ob[i], ob[i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i < nvalid) dst_b[o + i] = ob[i];
         }
     }
 }
 
 int launch_polyexp(const float* I, float* R, long long img_stride, int n_img, int h, int w, const PolyConsts& pc,
                    cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(polyexp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM_BYTES);
-        attr_set = true;
-    }
+    // (the attribute is per device: set it on every call, it is cheap)
+    cudaFuncSetAttribute(polyexp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PE_SMEM_BYTES);
     LaunchTimer lt(KC_POLYEXP, 24.0 * h * w * n_img, s, cdiv(n_img, 65535));
     for (int z0 = 0; z0 < n_img; z0 += 65535) {
         const int nz = min(n_img - z0, 65535);

@@ -496,33 +496,54 @@ __device__ __forceinline__ float2 upsample_one(const float2* __restrict__ r0, co
     return make_float2((ax * (1.f - fy) + cx * fy) * mul, (ay * (1.f - fy) + cy * fy) * mul);
 }
 
+// A block of 256 threads covers 512 columns x UP_ROWS rows of one field: cv::resize's double-precision source coordinates
+// are worked out once per block column / row into shared memory instead of per output.
+constexpr int UP_ROWS = 4;
 __global__ void __launch_bounds__(256) flow_upsample_kernel(const float2* __restrict__ src, float2* __restrict__ dst, int sh,
                                                             int sw, int h, int w, double scale_x, double scale_y,
                                                             float mul) {
-    const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-    const int j = blockIdx.y;
+    __shared__ int s_x0[512], s_x1[512], s_y0[UP_ROWS], s_y1[UP_ROWS];
+    __shared__ float s_fx[512], s_fy[UP_ROWS];
+    const int tid = threadIdx.x;
+    const int i = 2 * (blockIdx.x * blockDim.x + tid);
+    const int jb = blockIdx.y * UP_ROWS;
     const int f = blockIdx.z;
-    if (i >= w) return;
-    float2 o0 = make_float2(0.f, 0.f), o1 = o0;
     if (src != nullptr) {
-        int x0, x1, y0, y1; float fx, fy;
-        resize_coord(j, scale_y, sh, y0, y1, fy);
-        const float2* s = src + (long long)f * sh * sw;
-        const float2* r0 = s + (long long)y0 * sw;
-        const float2* r1 = s + (long long)y1 * sw;
-        resize_coord(i, scale_x, sw, x0, x1, fx);
-        o0 = upsample_one(r0, r1, x0, x1, fx, fy, mul);
-        if (i + 1 < w) {
-            resize_coord(i + 1, scale_x, sw, x0, x1, fx);
-            o1 = upsample_one(r0, r1, x0, x1, fx, fy, mul);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int c = 2 * tid + q;                   // block column
+            int a0, a1; float fr;
+            resize_coord(min(2 * (int)(blockIdx.x * blockDim.x) + c, w - 1), scale_x, sw, a0, a1, fr);
+            s_x0[c] = a0; s_x1[c] = a1; s_fx[c] = fr;
         }
+        if (tid < UP_ROWS) {
+            int a0, a1; float fr;
+            resize_coord(min(jb + tid, h - 1), scale_y, sh, a0, a1, fr);
+            s_y0[tid] = a0; s_y1[tid] = a1; s_fy[tid] = fr;
+        }
+        __syncthreads();
     }
-    float2* d = dst + ((long long)f * h + j) * w + i;
-    if (i + 1 < w && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
-        *reinterpret_cast<float4*>(d) = make_float4(o0.x, o0.y, o1.x, o1.y);
-    } else {
-        d[0] = o0;
-        if (i + 1 < w) d[1] = o1;
+    if (i >= w) return;
+    const float2* s = src ? src + (long long)f * sh * sw : nullptr;
+#pragma unroll
+    for (int r = 0; r < UP_ROWS; ++r) {
+        const int j = jb + r;
+        if (j >= h) break;
+        float2 o0 = make_float2(0.f, 0.f), o1 = o0;
+        if (src != nullptr) {
+            const float2* r0 = s + (long long)s_y0[r] * sw;
+            const float2* r1 = s + (long long)s_y1[r] * sw;
+            const float fy = s_fy[r];
+            o0 = upsample_one(r0, r1, s_x0[2 * tid], s_x1[2 * tid], s_fx[2 * tid], fy, mul);
+            if (i + 1 < w) o1 = upsample_one(r0, r1, s_x0[2 * tid + 1], s_x1[2 * tid + 1], s_fx[2 * tid + 1], fy, mul);
+        }
+        float2* d = dst + ((long long)f * h + j) * w + i;
+        if (i + 1 < w && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+            *reinterpret_cast<float4*>(d) = make_float4(o0.x, o0.y, o1.x, o1.y);
+        } else {
+            d[0] = o0;
+            if (i + 1 < w) d[1] = o1;
+        }
     }
 }
 
@@ -629,7 +650,7 @@ int launch_flow_upsample(const float* src, float* dst, int n_fields, int sh, int
     LaunchTimer lt(KC_UPSAMPLE, (8.0 * h * w + 8.0 * sh * sw) * n_fields, s, cdiv(n_fields, 65535));
     for (int z0 = 0; z0 < n_fields; z0 += 65535) {
         const int nz = min(n_fields - z0, 65535);
-        dim3 g(cdiv(cdiv(w, 2), 256), h, nz);
+        dim3 g(cdiv(cdiv(w, 2), 256), cdiv(h, UP_ROWS), nz);
         flow_upsample_kernel<<<g, 256, 0, s>>>(
             src ? reinterpret_cast<const float2*>(src) + (long long)z0 * sh * sw : nullptr,
             reinterpret_cast<float2*>(dst) + (long long)z0 * h * w, sh, sw, h, w, sx, sy, mul);
