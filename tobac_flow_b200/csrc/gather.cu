@@ -309,8 +309,11 @@ constexpr unsigned SB_S5 = (1u << 10) | (1u << 12) | (1u << 13) | (1u << 14) | (
 constexpr unsigned SB_L2 = (1u << 4) | (1u << 22);                                    // label.py:133-137
 constexpr unsigned SB_FULL = (1u << 27) - 1u;                                           // sobel
 
+#ifndef TF_GATHER_MINB
+#define TF_GATHER_MINB 4
+#endif
 template <typename SrcT, typename ST, int INTERP, int RC, unsigned SB>
-__global__ void __launch_bounds__(256) sl_gather_kernel(GatherArgs a) {
+__global__ void __launch_bounds__(256, (RC == RC_SOBEL ? TF_GATHER_MINB : 1)) sl_gather_kernel(GatherArgs a) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     const int t = blockIdx.z;
