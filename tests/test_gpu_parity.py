@@ -435,3 +435,26 @@ def test_float64_frames_are_normalised_in_float64():
     for mine, ref in ((f.forward_flow, rf), (f.backward_flow, rb)):
         e = np.sqrt(((mine - ref) ** 2).sum(-1))
         assert e.mean() <= 1e-3 and np.percentile(e, 99) <= 1e-2, (e.mean(), e.max())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# end rules on one-frame shards (tf_flow_finalise with T == 1: the last rank of a sharded run that owns one frame)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("first,last", [(0, 1), (1, 0), (1, 1), (0, 0)])
+@pytest.mark.parametrize("clamp_all", [False, True])
+def test_finalise_single_frame_shard(tfb, first, last, clamp_all):
+    import torch
+    from tobac_flow_b200.flow import finalise_flow_device
+    rng = np.random.default_rng(3)
+    f = (rng.standard_normal((1, 9, 11, 2)) * 30).astype(np.float32)
+    b = (rng.standard_normal((1, 9, 11, 2)) * 30).astype(np.float32)
+    ft, bt_ = torch.from_numpy(f.copy()).cuda(), torch.from_numpy(b.copy()).cuda()
+    finalise_flow_device(ft, bt_, 20.0, clamp_all, bool(first), bool(last))
+    ef, eb = f.copy(), b.copy()
+    if last:
+        ef[-1] = -eb[-1]          # flow.py:425
+    if first:
+        eb[0] = -ef[0]            # flow.py:426 (after :425, as in the reference)
+    if clamp_all:
+        ef, eb = np.clip(ef, -20, 20), np.clip(eb, -20, 20)
+    assert np.array_equal(ft.cpu().numpy(), ef) and np.array_equal(bt_.cpu().numpy(), eb)
