@@ -291,6 +291,20 @@ int tf_profile_reset(void);
 int tf_profile_read(int kernel_class, double* total_ms /* host */, double* total_bytes /* host */,
                     long long* launches /* host */);
 
+/*
+ * Semi-Lagrangian watershed flood: replaces tobac_flow._watershed.watershed_raveled (tobac_flow/_watershed.pyx:222-344) for
+ * the plain watershed of its only call site (tobac_flow/watershed.py:147-160: compactness 0, no watershed lines).
+ * ALL POINTERS ARE HOST POINTERS: the flood is a sequential priority queue ordered by (value, push age), as in the
+ * reference.  `image`, `mask` (int8, 0 = excluded; the padded border must be 0) and `output` (int32 labels, in/out: non-zero
+ * at the `n_markers` raveled `marker_locations`) have `n` elements; `structure[n_neighbors]` are the raveled neighbour
+ * offsets; `forward_offset` / `backward_offset` (n elements) the raveled rounded flow displacement of every pixel, added to
+ * the neighbours flagged in `forward_offset_locations` / `backward_offset_locations` (the t + 1 / t - 1 neighbours).
+ */
+int tf_watershed_flood_host(const float* image, const long long* marker_locations, long long n_markers,
+                            const long long* structure, int n_neighbors, const int* forward_offset,
+                            const int* backward_offset, const int* forward_offset_locations,
+                            const int* backward_offset_locations, const signed char* mask, int* output, long long n);
+
 #ifdef __cplusplus
 }
 #endif

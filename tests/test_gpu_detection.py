@@ -332,3 +332,32 @@ def test_growth_markers_float64_field(multi):
     assert np.array_equal(r["smoothed"].cpu().numpy(), want["smoothed"], equal_nan=True)
     assert np.array_equal(r["seeds"].cpu().numpy().astype(bool), want["seeds"])
     assert np.array_equal(r["markers"].cpu().numpy(), want["markers"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# watershed inputs: get_combined_edge_field / get_watershed_mask (the reference's tests/test_detection.py:17-60 restated)
+# ------------------------------------------------------------------------------------------------------------------
+def test_reference_get_combined_edge_field_and_watershed_mask():
+    import tobac_flow_b200 as tfb
+    from tobac_flow_b200.detection import get_combined_edge_field, get_watershed_mask
+    field = np.zeros([1, 5, 5], dtype=np.float32)
+    field[:, 3:] = 1
+    fl = tfb.Flow(np.zeros([1, 5, 5, 2], np.float32), np.zeros([1, 5, 5, 2], np.float32))
+    res = get_combined_edge_field(fl, field)
+    assert np.all(res[:, 2] > 0) and np.all(res[:, :2] == 0) and np.all(res[:, 3:] == -1)
+    field[:, :, 0] = np.nan
+    res = get_combined_edge_field(fl, field)
+    assert np.all(np.isnan(field) == np.isinf(res))
+    # get_watershed_mask (tests/test_detection.py:17-33): ones from row 2 on, eroded once
+    f2 = np.zeros([1, 5, 5], dtype=np.float32)
+    f2[:, 3:] = 1
+    m = get_watershed_mask(f2, erode_distance=1)
+    want = ndi.binary_erosion(np.logical_or(f2 <= 0, np.isnan(f2)), structure=np.ones([3, 3, 3]), iterations=1, border_value=1)
+    assert np.array_equal(m, want)
+    rng = np.random.default_rng(8)
+    f3 = rng.standard_normal((4, 30, 40)).astype(np.float32)
+    f3[rng.random(f3.shape) < 0.02] = np.nan
+    for it in (1, 2):
+        want = ndi.binary_erosion(np.logical_or(f3 <= 0, np.isnan(f3)), structure=np.ones([3, 3, 3]), iterations=it, border_value=1)
+        want[np.isnan(f3)] = True
+        assert np.array_equal(get_watershed_mask(f3, erode_distance=it), want)

@@ -27,6 +27,7 @@ EXPORTS = (
     "tf_ccl_workspace_bytes", "tf_flat_label", "tf_binary_fill_holes", "tf_gaussian_filter_yx", "tf_curvature_mask",
     "tf_binary_opening_cross", "tf_grey_opening_cross", "tf_scale_frames", "tf_mask_multiply", "tf_threshold_ge",
     "tf_label_max", "tf_label_overlap_count", "tf_label_link_groups", "tf_relabel", "tf_label_stats",
+    "tf_watershed_flood_host",
 )
 
 KERNEL_CLASSES = ("normalise", "pyramid", "polyexp", "flow_upsample", "fb_iter_coarse", "fb_iter_fullres",
@@ -119,6 +120,8 @@ def load():
                  "tf_binary_opening_cross", "tf_grey_opening_cross", "tf_scale_frames", "tf_mask_multiply",
                  "tf_threshold_ge", "tf_label_max", "tf_label_overlap_count", "tf_label_link_groups", "tf_relabel"):
         getattr(lib, name).restype = ci
+    lib.tf_watershed_flood_host.argtypes = [vp, vp, ll, vp, ci, vp, vp, vp, vp, vp, vp, ll]
+    lib.tf_watershed_flood_host.restype = ci
     lib.tf_profile_enable.argtypes = [ci]
     lib.tf_profile_read.argtypes = [ci, ctypes.POINTER(cd), ctypes.POINTER(cd), ctypes.POINTER(ll)]
     for name in ("tf_profile_enable", "tf_profile_reset", "tf_profile_read", "tf_fb_level_plan", "tf_fb_poly_constants", "tf_pair_normalise_u8", "tf_farneback_pairs",

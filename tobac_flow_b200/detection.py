@@ -246,3 +246,38 @@ def detect_growth_markers(flow, wvd):
         except Exception:
             pass
     return smoothed, markers
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# watershed inputs (detection.py:575-642): the edge field the anvil watershed floods, and its mask
+# ------------------------------------------------------------------------------------------------------------------
+def combined_edge_field_device(flow: Flow, field: torch.Tensor) -> torch.Tensor:
+    """``get_combined_edge_field`` (tobac_flow/detection.py:620-642) on a device tensor: uphill cubic flow-Sobel (fused
+    gather kernel, float64 like ``Flow.sobel``), ``+1`` where an edge exists, minus the field, ``inf`` where it is NaN."""
+    from .sobel import sobel_reducer
+    edges = flow.convolve(field, structure=np.ones((3, 3, 3), bool), method="cubic", fill_value=np.nan, dtype=None,
+                          func=sobel_reducer("uphill"))
+    edges = torch.where(edges > 0, edges + 1, edges)
+    edges = edges - field
+    return torch.where(torch.isnan(field), torch.full_like(edges, float("inf")), edges)
+
+
+def get_combined_edge_field(flow: Flow, field, **kwargs):
+    """``get_combined_edge_field`` (tobac_flow/detection.py:620-642); numpy in, numpy out."""
+    t, host = _to_device(_as_numpy(field) if not isinstance(field, torch.Tensor) else field)
+    res = combined_edge_field_device(flow, t)
+    return _to_host(res) if host else res
+
+
+def get_watershed_mask(field, erode_distance: int = 1):
+    """``get_watershed_mask`` (tobac_flow/detection.py:581-617): ``field <= 0`` or NaN, eroded ``erode_distance`` times with
+    the full 3x3x3 structure (border value 1), NaN pixels forced back to True."""
+    t, host = _to_device(_as_numpy(field) if not isinstance(field, torch.Tensor) else field)
+    nan = torch.isnan(t)
+    m = ((t <= 0) | nan).to(torch.float32)[None, None]
+    for _ in range(int(erode_distance)):
+        # binary erosion with a full structure and border_value = 1: the minimum over the 3x3x3 neighbourhood, the
+        # outside counting as 1 (max_pool3d pads with -inf)
+        m = -torch.nn.functional.max_pool3d(-m, kernel_size=3, stride=1, padding=1)
+    res = (m[0, 0] > 0.5) | nan
+    return res.cpu().numpy() if host else res

@@ -545,7 +545,13 @@ class Flow:
         return getattr(ref.Flow, name)(self, *args, **kwargs)
 
     def watershed(self, field, markers, mask=None, connectivity=1):
-        return self._delegate("watershed", field, markers, mask=mask, connectivity=connectivity)
+        """``Flow.watershed`` (tobac_flow/flow.py:236-279 -> tobac_flow/watershed.py:17-168): the offset fields are
+        prepared on the device, the (value, age) priority flood runs in the native library on the host."""
+        from .watershed import watershed
+        return watershed(self.forward_flow_device, self.backward_flow_device, _as_numpy(field) if not isinstance(field, torch.Tensor) else field.cpu().numpy(),
+                         _as_numpy(markers) if not isinstance(markers, torch.Tensor) else markers.cpu().numpy(),
+                         mask=None if mask is None else (_as_numpy(mask) if not isinstance(mask, torch.Tensor) else mask.cpu().numpy()),
+                         connectivity=connectivity)
 
     def label(self, data, structure=None, dtype: type = np.int32, overlap: float = 0, absolute_overlap: int = 1,
               subsegment_shrink: float = 0, peak_min_distance: int = 5):
