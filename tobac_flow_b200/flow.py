@@ -267,20 +267,30 @@ def recognise_reducer(func: Callable, n_taps: int, stack_dtype) -> int | None:
         return tagged
     if isinstance(func, partial) and func.func is np.any and func.keywords == {"axis": 0} and not func.args:
         return _lib.TF_RED_ANY
+    # Anything else is an anonymous callable: it is identified by behaviour.  TF_RECOGNISE_REDUCERS=0 switches this off
+    # (every untagged callable then takes the Python path); a substitution is announced once per reducer.
+    if os.environ.get("TF_RECOGNISE_REDUCERS", "1") == "0":
+        return None
     import warnings
     rng = np.random.default_rng(20240229)
     dt = np.dtype(np.float64 if stack_dtype is None else stack_dtype)
     probes = []
-    for _ in range(2):
-        x = rng.standard_normal((n_taps, 3, 4)) * 10
+    # magnitudes from unit scale to physical values with sentinels (a callable that clips at 150..350 K or masks
+    # values above 1000 before reducing differs from the plain reducer on these), infinities, NaNs and zeros
+    for scale, offset in ((10.0, 0.0), (40.0, 250.0), (3000.0, 0.0)):
+        x = rng.standard_normal((n_taps, 3, 4)) * scale + offset
         x[rng.random(x.shape) < 0.25] = np.nan
         x[:, 0, 0] = np.nan
         x[rng.random(x.shape) < 0.1] = 0
+        x[rng.random(x.shape) < 0.05] = 1.0e4
+        x[rng.random(x.shape) < 0.03] = -np.inf
+        x[rng.random(x.shape) < 0.03] = np.inf
         if dt.kind in "iub":
-            x = np.nan_to_num(x).astype(dt)
+            x = np.nan_to_num(x, posinf=30000, neginf=-30000).astype(dt)
         else:
             x = x.astype(dt)
         probes.append(x)
+    matched = None
     with warnings.catch_warnings(), np.errstate(all="ignore"):
         warnings.simplefilter("ignore")
         try:
@@ -296,8 +306,17 @@ def recognise_reducer(func: Callable, n_taps: int, stack_dtype) -> int | None:
                 continue
             if all(g.shape == w.shape and np.array_equal(g.astype(np.float64), w.astype(np.float64), equal_nan=True)
                    for g, w in zip(got, want)):
-                return code
-    return None
+                matched = code
+                break
+    if matched is not None and matched not in _ANNOUNCED:
+        _ANNOUNCED.add(matched)
+        warnings.warn(f"tobac_flow_b200: func={getattr(func, '__name__', func)!r} behaves like the built-in reducer "
+                      f"#{matched} on the probe stacks and runs as a fused CUDA reducer (TF_RECOGNISE_REDUCERS=0 keeps "
+                      "the Python callable)", stacklevel=3)
+    return matched
+
+
+_ANNOUNCED = set()
 
 
 def _tag(code):
@@ -748,6 +767,11 @@ def _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_meth
                               next_frames=frames_b[:T - 1], vr_steps=vr_steps)
     clamp_all = max_value is not None and (smoothing_passes > 0 or (bool(vr_steps) and vr_steps > 0))
     finalise_flow_device(fwd, bwd, max_value, clamp_all)
+    if max_value is not None and max_value == 0:
+        # np.minimum(np.maximum(f, -0), 0) (flow.py:60-61): every finite vector becomes 0 (the kernels read a zero clamp
+        # as "no clamp")
+        fwd = torch.where(torch.isnan(fwd), fwd, torch.zeros_like(fwd))
+        bwd = torch.where(torch.isnan(bwd), bwd, torch.zeros_like(bwd))
     return fwd, bwd
 
 
