@@ -114,3 +114,43 @@ def test_conus_growth_markers_vs_oracle(tfb):
     assert np.array_equal(r["linked"].cpu().numpy(), want["linked"])
     assert np.array_equal(r["markers"].cpu().numpy(), want["markers"])
     assert want["linked"].max() > 10
+
+
+@pytest.mark.parametrize("shape", [(3712, 3712), (5424, 5424)])
+def test_full_disk_stencils_vs_opencv_remap(tfb, shape):
+    """diff / sobel / convolve on one full-disk frame triple (SEVIRI 3712^2, GOES full disk 5424^2) against the oracle's
+    cv2.remap back-end, fed a synthetic but realistic flow (smooth, a few pixels, sub-pixel fractions, NaN pixels in the
+    data): diff and the 7-tap stack bit-exact, sobel within 1e-12 relative."""
+    import torch
+    h, w = shape
+    base = synthetic.base_field(h, w, 1238)
+    cores = synthetic.core_table(4, h, w, 1238)
+    plan = synthetic.nan_plan(4, h, w, 1238)
+    bt = np.stack([synthetic.bt_frame(base, t, cores, plan, 4) for t in (0, 1, 2)])
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    fx = (2.0 + 0.8 * np.sin(yy / 301.0) + 0.3 * np.cos(xx / 97.0)).astype(np.float32)
+    fy = (1.0 + 0.6 * np.cos(yy / 211.0) * np.sin(xx / 173.0)).astype(np.float32)
+    f1 = np.stack([fx, fy], -1)
+    fwd = np.stack([f1, f1, f1])
+    bwd = -fwd
+    fl = tfb.Flow(fwd, bwd)
+    s_diff = np.zeros((3, 3, 3)); s_diff[:, 1, 1] = 1
+    s_cross = np.zeros((3, 3, 3)); s_cross[1, 1, :] = s_cross[1, :, 1] = s_cross[:, 1, 1] = 1
+    got_d = fl.diff(bt)[1]
+    want_d = ops.diff_reducer(ops.tap_stack(bt[0], bt[1], bt[2], fwd[1], bwd[1], s_diff, "linear", np.float32, np.nan, BACKEND))
+    want_d[np.isnan(bt[1])] = np.nan
+    assert np.array_equal(got_d, want_d, equal_nan=True)
+    del got_d, want_d
+    got_c = fl.convolve(bt)[:, 1]
+    want_c = ops.tap_stack(bt[0], bt[1], bt[2], fwd[1], bwd[1], s_cross, "linear", np.float32, np.nan, BACKEND)
+    assert np.array_equal(got_c, want_c, equal_nan=True)
+    del got_c, want_c
+    got_s = fl.sobel(bt)[1]
+    want_s = ops.sobel_reducer(None)(ops.tap_stack(bt[0], bt[1], bt[2], fwd[1], bwd[1], np.ones((3, 3, 3)), "linear",
+                                                   np.float64, np.nan, BACKEND))
+    want_s[np.isnan(bt[1])] = np.nan
+    assert np.array_equal(np.isnan(got_s), np.isnan(want_s))
+    m = ~np.isnan(want_s)
+    assert np.max(np.abs(got_s[m] - want_s[m]) / np.maximum(np.abs(want_s[m]), 1)) < 1e-12
+    del fl
+    torch.cuda.empty_cache()
