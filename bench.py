@@ -63,7 +63,7 @@ def parse_args():
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record at N > 1")
-    ap.add_argument("--e2e-frames", type=int, default=96)
+    ap.add_argument("--e2e-frames", type=int, default=288, help="frames per end-to-end step (bounded by host memory)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -507,7 +507,16 @@ def run_b200(args):
     # ---- end to end through the public numpy API with host buffers ---------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        Te = min(args.e2e_frames, T)
+        # every result of a step lands in page-locked host memory (164 MB per CONUS frame): keep all ranks of the box
+        # together within half of the available RAM
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 64 << 30
+        n_local = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        per_frame = N * (4 + 4 + 8 + 28) + 1
+        Te = max(4, min(args.e2e_frames, T, int(avail * 0.5 / n_local / per_frame)))
         host_in = torch.empty((Te, H, W), dtype=torch.float32, pin_memory=True)
         host_in.copy_(shard.buf[1:1 + Te])
         torch.cuda.synchronize()

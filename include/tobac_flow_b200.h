@@ -94,6 +94,12 @@ int tf_fb_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int H
 long long tf_fb_r_stride(int h, int w);
 int tf_fb_polyexp(const float* I, int n_img, int h, int w, const tf_fb_params* p /* host */, float* R, void* stream);
 
+/* Which fused-iteration kernel tf_farneback_pairs launches: 3 = the default (TMA-staged rows, tensor-memory ring, packed
+ * fp32, two rows of gathers in flight), 4 = the same with one row in flight, 0 = the scalar LDG / shared-memory kernel,
+ * 1 = the scalar kernel with its ring in tensor memory.  For A/B measurements and cross-check tests; the environment
+ * variable TF_TMA sets the initial choice. */
+int tf_fb_select_kernel(int which);
+
 /* Bytes of scratch tf_farneback_pairs needs for `n_pairs` pairs of H x W frames. */
 size_t tf_farneback_workspace_bytes(int n_pairs, int H, int W, const tf_fb_params* p /* host */);
 

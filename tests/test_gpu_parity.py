@@ -458,3 +458,29 @@ def test_finalise_single_frame_shard(tfb, first, last, clamp_all):
     if clamp_all:
         ef, eb = np.clip(ef, -20, 20), np.clip(eb, -20, 20)
     assert np.array_equal(ft.cpu().numpy(), ef) and np.array_equal(bt_.cpu().numpy(), eb)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the default iteration kernel (TMA-staged, tensor-memory ring, packed fp32) against the scalar LDG kernel
+# ------------------------------------------------------------------------------------------------------------------
+def test_iteration_kernels_agree(tfb):
+    """Both kernels form the same window sums bit for bit; they differ only in the reciprocal of the determinant (one
+    MUFU.RCP, <= 1 ulp, against an IEEE division), so the flows agree to a few ulp of a pixel; odd sizes exercise the
+    general alignment path (WAL = 0 / 1) and strips narrower than the halo."""
+    from tobac_flow_b200 import _lib
+    lib = _lib.load()
+    try:
+        for shape in ((3, 100, 100), (3, 97, 131), (2, 150, 258), (2, 64, 1101)):
+            bt = synthetic.bt_sequence(shape[0], shape[1], shape[2], seed=77 + shape[2], nans=True)
+            res = {}
+            for k in (0, 1, 3, 4):
+                _lib.check(lib.tf_fb_select_kernel(k), "tf_fb_select_kernel")
+                f = tfb.create_flow(bt)
+                res[k] = (f.forward_flow.copy(), f.backward_flow.copy())
+            assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])   # ring placement only
+            assert np.array_equal(res[3][0], res[4][0]) and np.array_equal(res[3][1], res[4][1])   # lookahead depth only
+            for a, b in zip(res[0], res[3]):
+                assert np.abs(a - b).max() <= 2e-5, np.abs(a - b).max()
+        assert lib.tf_fb_select_kernel(2) < 0
+    finally:
+        lib.tf_fb_select_kernel(3)

@@ -20,7 +20,7 @@ TF_NEAREST, TF_LINEAR, TF_CUBIC = 0, 1, 2
 # every symbol include/tobac_flow_b200.h declares
 EXPORTS = (
     "tf_version", "tf_last_error", "tf_fb_default_params", "tf_fb_level_plan", "tf_fb_poly_constants",
-    "tf_fb_pyramid_level", "tf_fb_r_stride", "tf_fb_polyexp",
+    "tf_fb_pyramid_level", "tf_fb_r_stride", "tf_fb_polyexp", "tf_fb_select_kernel",
     "tf_farneback_workspace_bytes", "tf_pair_normalise_u8", "tf_pair_normalise_u8_f64", "tf_farneback_pairs", "tf_smooth_flow_step",
     "tf_flow_finalise", "tf_sl_convolve", "tf_profile_enable", "tf_profile_reset", "tf_profile_read",
     "tf_vr_default_params", "tf_vr_workspace_bytes", "tf_variational_refinement",
@@ -83,6 +83,8 @@ def load():
     lib.tf_fb_r_stride.restype = ll
     lib.tf_fb_polyexp.argtypes = [vp, ci, ci, ci, pp, vp, vp]
     lib.tf_fb_polyexp.restype = ci
+    lib.tf_fb_select_kernel.argtypes = [ci]
+    lib.tf_fb_select_kernel.restype = ci
     lib.tf_pair_normalise_u8.argtypes = [vp, vp, ll, vp, vp, ci, ci, ci, vp, vp]
     lib.tf_pair_normalise_u8_f64.argtypes = lib.tf_pair_normalise_u8.argtypes
     lib.tf_pair_normalise_u8_f64.restype = ci
