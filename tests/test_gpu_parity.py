@@ -484,3 +484,16 @@ def test_iteration_kernels_agree(tfb):
         assert lib.tf_fb_select_kernel(2) < 0
     finally:
         lib.tf_fb_select_kernel(3)
+
+
+def test_host_results_beyond_the_pinned_cap(tfb, golden, monkeypatch):
+    """Results larger than TF_PINNED_RESULT_MAX_GB are staged through two pinned chunks into an ordinary numpy array:
+    same values as the page-locked path."""
+    g = golden("bt_small")
+    bt = cases.small_bt()
+    fl = tfb.Flow(g["fwd"], g["bwd"])
+    want_d, want_c = fl.diff(bt), fl.convolve(bt)
+    monkeypatch.setenv("TF_PINNED_RESULT_MAX_GB", "0")
+    got_d, got_c = fl.diff(bt), fl.convolve(bt)
+    assert_same(got_d, want_d)
+    assert_same(got_c, want_c)

@@ -94,6 +94,16 @@ def _to_host(t: torch.Tensor) -> np.ndarray:
     return h.numpy()
 
 
+def _pinned_result_cap() -> int:
+    gb = os.environ.get("TF_PINNED_RESULT_MAX_GB")
+    if gb is not None:
+        return int(float(gb) * (1 << 30))
+    try:
+        return os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") // 4
+    except (ValueError, OSError):
+        return 32 << 30
+
+
 _HOST_CHUNK_BYTES = 192 << 20     # result bytes per pipelined chunk of the host path
 _HOST_PAIR_BATCH = 8              # pairs per launch batch while a host operand is still being uploaded
 _SIDE_STREAMS = {}
@@ -465,9 +475,16 @@ class Flow:
         T, H, W = src.shape
         out_t, _ = _dtype_code(dtype)
         stack = reducer == _lib.TF_RED_NONE
-        host = torch.empty((n_taps, T, H, W) if stack else (T, H, W), dtype=out_t, pin_memory=True)
+        # Results land in page-locked memory (a pageable target halves the PCIe rate).  torch's pinned allocator never
+        # returns blocks to the OS, so results beyond the cap (TF_PINNED_RESULT_MAX_GB, default a quarter of the host RAM)
+        # go to an ordinary numpy array through two pinned staging chunks instead.
+        shape_all = (n_taps, T, H, W) if stack else (T, H, W)
+        nbytes_all = int(np.prod(shape_all)) * out_t.itemsize
+        pinned = nbytes_all <= _pinned_result_cap()
+        host = torch.empty(shape_all, dtype=out_t, pin_memory=pinned)
         if T == 0:
             return host.numpy()
+        stage, ev_stage, pending = [None, None], [None, None], [None, None]
         fwd, bwd = self.forward_flow_device, self.backward_flow_device
         per_frame = H * W * out_t.itemsize * (n_taps if stack else 1)
         # chunks of at most _HOST_CHUNK_BYTES of result, and at least four of them so that upload, kernels and download
@@ -507,15 +524,33 @@ class Flow:
             ev_c = torch.cuda.Event()
             ev_c.record(cur)
             s_out.wait_event(ev_c)
+            if not pinned:
+                # flush the staging chunk this slot used two chunks ago into the pageable result (host-side copy)
+                if pending[slot] is not None:
+                    ev_stage[slot].synchronize()
+                    pa, pb = pending[slot]
+                    host[(slice(None), slice(pa, pb)) if stack else slice(pa, pb)] = stage[slot][(slice(None), slice(0, pb - pa)) if stack else slice(0, pb - pa)]
+                if stage[slot] is None or stage[slot].shape[1 if stack else 0] < n:
+                    stage[slot] = torch.empty((n_taps, Tc, H, W) if stack else (Tc, H, W), dtype=out_t, pin_memory=True)
             with torch.cuda.stream(s_out):
+                tgt = host if pinned else stage[slot]
+                off = a0 if pinned else 0
                 if stack:
                     for tap in range(n_taps):
-                        host[tap, a0:b0].copy_(bufs[slot][tap], non_blocking=True)
+                        tgt[tap, off:off + n].copy_(bufs[slot][tap], non_blocking=True)
                 else:
-                    host[a0:b0].copy_(bufs[slot], non_blocking=True)
+                    tgt[off:off + n].copy_(bufs[slot], non_blocking=True)
                 ev_free[slot] = torch.cuda.Event()
                 ev_free[slot].record(s_out)
+                if not pinned:
+                    ev_stage[slot] = ev_free[slot]
+                    pending[slot] = (a0, b0)
         s_out.synchronize()
+        if not pinned:
+            for slot in (0, 1):
+                if pending[slot] is not None:
+                    pa, pb = pending[slot]
+                    host[(slice(None), slice(pa, pb)) if stack else slice(pa, pb)] = stage[slot][(slice(None), slice(0, pb - pa)) if stack else slice(0, pb - pa)]
         cur.wait_stream(s_in)
         if resident is None:
             _OPERANDS.put(a, d_in)
