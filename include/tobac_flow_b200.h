@@ -38,7 +38,7 @@ typedef enum tf_status {
 typedef enum tf_dtype { TF_F32 = 0, TF_F64 = 1, TF_I32 = 2 } tf_dtype;
 
 /* cv2.remap interpolation modes used by tobac_flow/convolve.py:46-54 */
-typedef enum tf_interp { TF_NEAREST = 0, TF_LINEAR = 1, TF_CUBIC = 2 } tf_interp;
+typedef enum tf_interp { TF_NEAREST = 0, TF_LINEAR = 1, TF_CUBIC = 2, TF_LANCZOS4 = 3 } tf_interp;
 
 /* per-step reducers (`func=`) the reference and its callers apply to the (n_taps, H, W) tap stack */
 typedef enum tf_reducer {

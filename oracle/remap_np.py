@@ -5,7 +5,7 @@ reference calls it at ``tobac_flow/convolve.py:65-84`` and ``tobac_flow/utils/fl
 
 The arithmetic lives in OpenCV (not vendored in /root/reference; image has 4.13.0).  Restated from
 opencv/modules/imgproc/src/imgwarp.cpp (remap, remapNearest, remapBilinear, remapBicubic,
-interpolateLinear/Cubic, initInterTab2D):
+interpolateLinear/Cubic/Lanczos4, remapLanczos4, initInterTab2D):
 
 * float maps are converted to fixed point: s = cvRound(coord * 32) (round half even), integer part
   s >> 5, fraction (s & 31) / 32;  nearest uses cvRound(coord) with no sub-pixel part;
@@ -148,7 +148,63 @@ def remap(src: np.ndarray, mapx: np.ndarray, mapy: np.ndarray, method: str = "li
         out = np.where(fast, acc_fast, acc_b)
         return np.where(outside & ~fast, cv, out).astype(src.dtype)
 
-    raise NotImplementedError("lanczos interpolation is not restated in the oracle")
+    # lanczos (cv2.INTER_LANCZOS4, remapLanczos4): 8 x 8 taps from (ix - 3, iy - 3), table weights wy[k1] * wx[k2] in fp32;
+    # inside: sum += (eight-term row expression, left to right) row by row; near the border: cv + sum (S - cv) * w over
+    # the in-bounds taps in row-major order; entirely outside: cv
+    tab = lanczos4_table()
+    cx = tab[fxi]
+    cy = tab[fyi]
+    x0 = ix - 3
+    y0 = iy - 3
+    fast = (x0 >= 0) & (x0 < max(W - 7, 0)) & (y0 >= 0) & (y0 < max(H - 7, 0))
+    outside = (x0 >= W) | (x0 + 8 <= 0) | (y0 >= H) | (y0 + 8 <= 0)
+    with np.errstate(invalid="ignore", over="ignore"):
+        acc_fast = np.zeros(mapx.shape, dtype=wt)
+        acc_b = cv * np.ones(mapx.shape, dtype=wt)
+        for k1 in range(8):
+            yy = y0 + k1
+            yin = (yy >= 0) & (yy < H)
+            row = None
+            for k2 in range(8):
+                xx = x0 + k2
+                xin = (xx >= 0) & (xx < W)
+                w = (cy[..., k1] * cx[..., k2]).astype(F32).astype(wt)
+                sv = src[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)].astype(wt)
+                t = sv * w
+                row = t if row is None else row + t
+                acc_b = np.where(yin & xin, acc_b + (sv - cv) * w, acc_b)
+            acc_fast = acc_fast + row
+    out = np.where(fast, acc_fast, acc_b)
+    return np.where(outside & ~fast, cv, out).astype(src.dtype)
+
+
+_LANCZOS_TAB = None
+
+
+def lanczos4_table() -> np.ndarray:
+    """interpolateLanczos4 for the 32 table fractions (imgwarp.cpp): eight fp32 coefficients per fraction, sines / cosines
+    in double, normalised in fp32."""
+    global _LANCZOS_TAB
+    if _LANCZOS_TAB is not None:
+        return _LANCZOS_TAB
+    import math
+    s45 = 0.70710678118654752440084436210485
+    cs = [(1, 0), (-s45, -s45), (0, 1), (s45, -s45), (-1, 0), (s45, s45), (0, -1), (-s45, s45)]
+    tab = np.zeros((32, 8), F32)
+    tab[0, 3] = 1            # x < FLT_EPSILON: the centre tap alone
+    for i in range(1, 32):
+        x = F32(F32(i) * F32(1.0 / 32.0))
+        y0 = -(float(x) + 3) * math.pi * 0.25
+        s0, c0 = math.sin(y0), math.cos(y0)
+        co = np.zeros(8, F32)
+        ssum = F32(0)
+        for k in range(8):
+            y = -float(F32(F32(x + F32(3)) - F32(k))) * math.pi * 0.25
+            co[k] = F32((cs[k][0] * s0 + cs[k][1] * c0) / (y * y))
+            ssum = F32(ssum + co[k])
+        tab[i] = (co * F32(F32(1) / ssum)).astype(F32)
+    _LANCZOS_TAB = tab
+    return tab
 
 
 def warp_positions(flow: np.ndarray, dx: int = 0, dy: int = 0):

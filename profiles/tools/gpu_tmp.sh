@@ -1,6 +1,6 @@
 #!/bin/bash
-rm -f gpurun_out/ab.log
-timeout 900 python -m pytest tests/test_gpu_stages.py tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/d_tests.log 2>&1
-echo "rc $?" >> gpurun_out/d_tests.log; tail -4 gpurun_out/d_tests.log
-bash profiles/tools/ab.sh "TF_X=1" "TF_PYR_NO_EXACT=1" > gpurun_out/d_ab_stdout.log 2>&1
-grep -E "===|fps|pyramid" gpurun_out/ab.log
+timeout 1700 python -m pytest tests -x -q -m gpu > gpurun_out/e_tests.log 2>&1
+echo "rc $?" >> gpurun_out/e_tests.log; tail -5 gpurun_out/e_tests.log
+python bench.py --frames 8 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-detection > gpurun_out/e_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'fb_iter|sl_gather|polyexp|blur|flow_upsample|flow_finalise|pair_|minmax' -c 400 --csv --log-file gpurun_out/launches_r2.csv python bench.py --frames 8 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-detection > gpurun_out/e_ncu.log 2>&1
+tail -1 gpurun_out/e_ncu.log

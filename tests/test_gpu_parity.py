@@ -497,3 +497,27 @@ def test_host_results_beyond_the_pinned_cap(tfb, golden, monkeypatch):
     got_d, got_c = fl.diff(bt), fl.convolve(bt)
     assert_same(got_d, want_d)
     assert_same(got_c, want_c)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# lanczos interpolation (cv2.INTER_LANCZOS4; convolve.py:46-51): bit-exact against the oracle (itself bit-exact vs cv2)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_lanczos_gather_bit_exact(tfb, golden, dtype):
+    g = golden("bt_small")
+    bt = cases.small_bt().astype(dtype)
+    fl = tfb.Flow(g["fwd"], g["bwd"])
+    for fill in (np.nan, 0.0):
+        got = fl.convolve(bt, method="lanczos", fill_value=fill, dtype=dtype)
+        want = ops.convolve(bt, g["fwd"], g["bwd"], method="lanczos", dtype=dtype, fill_value=fill)
+        assert_same(got, want)
+    # wild flows: taps leave the image, whole footprints outside
+    rng = np.random.default_rng(17)
+    wild_f = (g["fwd"] + rng.standard_normal(g["fwd"].shape).astype(np.float32) * 15).astype(np.float32)
+    wild_b = (g["bwd"] + rng.standard_normal(g["bwd"].shape).astype(np.float32) * 15).astype(np.float32)
+    fw = tfb.Flow(wild_f, wild_b)
+    assert_same(fw.diff(bt.astype(np.float32), method="lanczos"), ops.diff(bt.astype(np.float32), wild_f, wild_b, method="lanczos"))
+    f, b = tfb.smooth_flow_step(g["fwd"][0], g["bwd"][1], method="lanczos")
+    rf, rb = ops.smooth_flow_step(g["fwd"][0], g["bwd"][1], "lanczos")
+    assert_same(f, rf)
+    assert_same(b, rb)

@@ -44,11 +44,11 @@ def test_quantisation_and_rounding():
 
 @pytest.mark.skipif(not flow_ops.have_cv2(), reason="cv2 not importable")
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("method", ["nearest", "linear", "cubic"])
+@pytest.mark.parametrize("method", ["nearest", "linear", "cubic", "lanczos"])
 @pytest.mark.parametrize("fill", [np.nan, 0.0, -3.5])
 def test_bit_exact_vs_cv2(dtype, method, fill):
     import cv2
-    code = dict(nearest=cv2.INTER_NEAREST, linear=cv2.INTER_LINEAR, cubic=cv2.INTER_CUBIC)[method]
+    code = dict(nearest=cv2.INTER_NEAREST, linear=cv2.INTER_LINEAR, cubic=cv2.INTER_CUBIC, lanczos=cv2.INTER_LANCZOS4)[method]
     rng = np.random.default_rng(11)
     H, W = 61, 203
     src = (rng.standard_normal((H, W)) * 100).astype(dtype)
@@ -73,3 +73,20 @@ def test_int32_nearest_vs_cv2():
     px, py = rm.warp_positions(flow)
     ref = cv2.remap(src, np.stack([px, py], -1), None, cv2.INTER_NEAREST, None, cv2.BORDER_CONSTANT, 0)
     assert np.array_equal(ref, rm.remap(src, px, py, "nearest", 0))
+
+
+@pytest.mark.skipif(not flow_ops.have_cv2(), reason="cv2 not importable")
+@pytest.mark.parametrize("shape", [(3, 5), (8, 8), (1, 9), (9, 64)])
+def test_lanczos_small_images_vs_cv2(shape):
+    """Images smaller than the 8 x 8 kernel and sampling positions with zero fraction (the centre-tap-only table row)."""
+    import cv2
+    rng = np.random.default_rng(5)
+    H, W = shape
+    src = rng.standard_normal((H, W)).astype(np.float32)
+    mapx = rng.uniform(-6, W + 5, (40, 50)).astype(np.float32)
+    mapy = rng.uniform(-6, H + 5, (40, 50)).astype(np.float32)
+    mapx[::7, ::5] = np.round(mapx[::7, ::5])
+    mapy[::3, ::11] = np.round(mapy[::3, ::11])
+    for fill in (np.nan, 0.0):
+        ref = cv2.remap(src, np.stack([mapx, mapy], -1), None, cv2.INTER_LANCZOS4, None, cv2.BORDER_CONSTANT, fill)
+        assert np.array_equal(ref, rm.remap(src, mapx, mapy, "lanczos", fill), equal_nan=True)

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TF_LIB_PATH") or os.path.join(HERE, "libtobacflow_b200.so")
 
 TF_F32, TF_F64, TF_I32 = 0, 1, 2
-TF_NEAREST, TF_LINEAR, TF_CUBIC = 0, 1, 2
+TF_NEAREST, TF_LINEAR, TF_CUBIC, TF_LANCZOS4 = 0, 1, 2, 3
 (TF_RED_NONE, TF_RED_DIFF, TF_RED_NANMEAN, TF_RED_ANY, TF_RED_SOBEL, TF_RED_SOBEL_UPHILL,
  TF_RED_SOBEL_DOWNHILL, TF_RED_NANMAX, TF_RED_NANMIN) = range(9)
 

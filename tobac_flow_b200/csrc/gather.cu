@@ -8,6 +8,7 @@
 //
 // One thread per output pixel; the tap stack lives in registers only.  HBM traffic per pixel-step: 3 operand frames
 // (neighbour re-reads hit L1/L2), 2 flow fields (16 B) and the result.
+#include <mutex>
 #include <type_traits>
 
 #include "tf_common.cuh"
@@ -73,6 +74,10 @@ __device__ __forceinline__ void cubic_coeffs(int fi, float c[4]) {
     c[3] = __fsub_rn(__fsub_rn(__fsub_rn(1.f, c[0]), c[1]), c[2]);
 }
 
+// cv2.INTER_LANCZOS4: the 32 x 8 fp32 coefficient table of interpolateLanczos4 (imgwarp.cpp), built on the host exactly as
+// OpenCV builds it (sines / cosines in double from the same libm, normalisation in fp32) and kept in constant memory
+__constant__ float c_lanczos4[32 * 8];
+
 // cv2.remap at one position.  T: element type, Src: accessor with at(y, x), H, W, fill
 template <int INTERP, typename T, typename Src>
 __device__ __forceinline__ T remap_at(const Src& s, float px, float py) {
@@ -102,6 +107,39 @@ __device__ __forceinline__ T remap_at(const Src& s, float px, float py) {
                 v11 = (y1 && x1) ? s.at(iy + 1, ix + 1) : s.fill;
             }
             return add_rn(add_rn(add_rn(mul_rn(v00, w00), mul_rn(v01, w01)), mul_rn(v10, w10)), mul_rn(v11, w11));
+        } else if constexpr (INTERP == TF_LANCZOS4) {
+            // remapLanczos4: 8 x 8 taps from (ix - 3, iy - 3); weights wy[k1] * wx[k2] (fp32 table product); inside: the
+            // eight-term row expression left to right, rows added in order; near the border: cv + sum (S - cv) * w
+            const float* cx = c_lanczos4 + 8 * fxi;
+            const float* cy = c_lanczos4 + 8 * fyi;
+            const int x0 = ix - 3, y0 = iy - 3;
+            if ((unsigned)x0 < (unsigned)max(W - 7, 0) && (unsigned)y0 < (unsigned)max(H - 7, 0)) {
+                T sum = (T)0;
+#pragma unroll 1
+                for (int k1 = 0; k1 < 8; ++k1) {
+                    T row = mul_rn(s.at(y0 + k1, x0), (T)__fmul_rn(cy[k1], cx[0]));
+#pragma unroll
+                    for (int k2 = 1; k2 < 8; ++k2)
+                        row = add_rn(row, mul_rn(s.at(y0 + k1, x0 + k2), (T)__fmul_rn(cy[k1], cx[k2])));
+                    sum = add_rn(sum, row);
+                }
+                return sum;
+            }
+            if (x0 >= W || x0 + 8 <= 0 || y0 >= H || y0 + 8 <= 0) return s.fill;
+            const T cv = s.fill;
+            T sum = cv;
+#pragma unroll 1
+            for (int k1 = 0; k1 < 8; ++k1) {
+                const int yy = y0 + k1;
+                if ((unsigned)yy >= (unsigned)H) continue;
+#pragma unroll 1
+                for (int k2 = 0; k2 < 8; ++k2) {
+                    const int xx = x0 + k2;
+                    if ((unsigned)xx < (unsigned)W)
+                        sum = add_rn(sum, mul_rn(sub_rn(s.at(yy, xx), cv), (T)__fmul_rn(cy[k1], cx[k2])));
+                }
+            }
+            return sum;
         } else {  // cubic
             float cx[4], cy[4];
             cubic_coeffs(fxi, cx);
@@ -466,6 +504,7 @@ static int dispatch_interp(const GatherArgs& a, int interp, int rc, cudaStream_t
     switch (interp) {
         case TF_NEAREST: return dispatch_rc<SrcT, ST, TF_NEAREST>(a, rc, s);
         case TF_LINEAR: return dispatch_rc<SrcT, ST, TF_LINEAR>(a, rc, s);
+        case TF_LANCZOS4: return dispatch_rc<SrcT, ST, TF_LANCZOS4>(a, rc, s);
         default: return dispatch_rc<SrcT, ST, TF_CUBIC>(a, rc, s);
     }
 }
@@ -522,6 +561,41 @@ __global__ void __launch_bounds__(256) flow_finalise_kernel(float* __restrict__ 
     bwd[o] = b;
 }
 
+// interpolateLanczos4 for the 32 table fractions; uploaded once per device
+static int upload_lanczos4_table() {
+    static std::mutex mu;
+    static unsigned long long done_mask = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("lanczos table: no CUDA device"); return TF_ERR_CUDA; }
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 64 && ((done_mask >> dev) & 1ull)) return TF_OK;
+    static const double s45 = 0.70710678118654752440084436210485;
+    static const double cs[8][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+    const double pi = 3.1415926535897932384626433832795;     // CV_PI
+    float tab[32 * 8];
+    for (int i = 0; i < 32 * 8; ++i) tab[i] = 0.f;
+    tab[3] = 1.f;                                             // x < FLT_EPSILON: the centre tap alone
+    for (int i = 1; i < 32; ++i) {
+        const float x = (float)i * (1.f / 32.f);
+        float* co = tab + 8 * i;
+        float sum = 0.f;
+        const double y0 = -(x + 3) * pi * 0.25, s0 = sin(y0), c0 = cos(y0);
+        for (int k = 0; k < 8; ++k) {
+            const double y = -(x + 3 - k) * pi * 0.25;        // (x + 3 - k) in float, as in OpenCV
+            co[k] = (float)((cs[k][0] * s0 + cs[k][1] * c0) / (y * y));
+            sum += co[k];
+        }
+        sum = 1.f / sum;
+        for (int k = 0; k < 8; ++k) co[k] *= sum;
+    }
+    if (cudaMemcpyToSymbol(c_lanczos4, tab, sizeof(tab)) != cudaSuccess) {
+        set_error("lanczos table: cudaMemcpyToSymbol failed");
+        return TF_ERR_CUDA;
+    }
+    if (dev < 64) done_mask |= 1ull << dev;
+    return TF_OK;
+}
+
 }  // namespace tf
 
 using namespace tf;
@@ -535,7 +609,8 @@ extern "C" int tf_sl_convolve(const void* cur0, int n_frames, int has_prev, int 
         set_error("tf_sl_convolve: invalid argument");
         return TF_ERR_INVALID_ARGUMENT;
     }
-    if (interp < TF_NEAREST || interp > TF_CUBIC) { set_error("tf_sl_convolve: unknown interpolation %d", interp); return TF_ERR_INVALID_ARGUMENT; }
+    if (interp < TF_NEAREST || interp > TF_LANCZOS4) { set_error("tf_sl_convolve: unknown interpolation %d", interp); return TF_ERR_INVALID_ARGUMENT; }
+    if (interp == TF_LANCZOS4) { const int rc_l = upload_lanczos4_table(); if (rc_l != TF_OK) return rc_l; }
     if (reducer < TF_RED_NONE || reducer > TF_RED_NANMIN) { set_error("tf_sl_convolve: unknown reducer %d", reducer); return TF_ERR_INVALID_ARGUMENT; }
     GatherArgs a{};
     a.cur0 = cur0; a.fflow0 = reinterpret_cast<const float2*>(fflow0); a.bflow0 = reinterpret_cast<const float2*>(bflow0);
@@ -608,6 +683,10 @@ extern "C" int tf_smooth_flow_step(const float* fwd, const float* bwd, float* fw
             case TF_NEAREST: smooth_flow_kernel<TF_NEAREST><<<grid, block, 0, s>>>(f, b, fo, bo, stride, H, W); break;
             case TF_LINEAR: smooth_flow_kernel<TF_LINEAR><<<grid, block, 0, s>>>(f, b, fo, bo, stride, H, W); break;
             case TF_CUBIC: smooth_flow_kernel<TF_CUBIC><<<grid, block, 0, s>>>(f, b, fo, bo, stride, H, W); break;
+            case TF_LANCZOS4:
+                if (upload_lanczos4_table() != TF_OK) return TF_ERR_CUDA;
+                smooth_flow_kernel<TF_LANCZOS4><<<grid, block, 0, s>>>(f, b, fo, bo, stride, H, W);
+                break;
             default: set_error("tf_smooth_flow_step: unknown interpolation %d", interp); return TF_ERR_INVALID_ARGUMENT;
         }
     }

@@ -23,7 +23,7 @@ import torch
 from . import _lib
 from ._lib import NativeError  # noqa: F401  (re-export)
 
-_INTERP = {"nearest": _lib.TF_NEAREST, "linear": _lib.TF_LINEAR, "cubic": _lib.TF_CUBIC}
+_INTERP = {"nearest": _lib.TF_NEAREST, "linear": _lib.TF_LINEAR, "cubic": _lib.TF_CUBIC, "lanczos": _lib.TF_LANCZOS4}
 _REFERENCE_INTERP_NAMES = ["nearest", "linear", "cubic", "lanczos"]  # convolve.py:46-51
 _REFERENCE_MODELS = ["Farneback", "DeepFlow", "PCA", "SimpleFlow", "SparseToDense", "DIS", "DenseRLOF", "DualTVL1"]
 _NORMALISATIONS = ["linear", "log", "inverse_log", "z_score", "uniform", "local_linear"]
