@@ -1,6 +1,13 @@
 #!/bin/bash
-timeout 1700 python -m pytest tests -x -q -m gpu > gpurun_out/e_tests.log 2>&1
-echo "rc $?" >> gpurun_out/e_tests.log; tail -5 gpurun_out/e_tests.log
-python bench.py --frames 8 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-detection > gpurun_out/e_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'fb_iter|sl_gather|polyexp|blur|flow_upsample|flow_finalise|pair_|minmax' -c 400 --csv --log-file gpurun_out/launches_r2.csv python bench.py --frames 8 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-detection > gpurun_out/e_ncu.log 2>&1
-tail -1 gpurun_out/e_ncu.log
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
+timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu > gpurun_out/f_multi_tests.log 2>&1
+echo "rc $?" >> gpurun_out/f_multi_tests.log; tail -3 gpurun_out/f_multi_tests.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 8 --steps 2 --warmup 3 > gpurun_out/bench_r2_8gpu.json 2> gpurun_out/bench_r2_8gpu.err
+echo "bench rc $?"; tail -3 gpurun_out/bench_r2_8gpu.err | cut -c1-300
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_r2_8gpu.json').read().strip().splitlines()[-1])
+print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e'],'parity',d.get('sharded_parity'),'strong',d.get('strong'))
+print(d['config']['host_pinning'], d['clocks'])
+PY
