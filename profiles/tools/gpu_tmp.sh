@@ -1,13 +1,13 @@
 #!/bin/bash
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu > gpurun_out/f_multi_tests.log 2>&1
-echo "rc $?" >> gpurun_out/f_multi_tests.log; tail -3 gpurun_out/f_multi_tests.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 8 --steps 2 --warmup 3 > gpurun_out/bench_r2_8gpu.json 2> gpurun_out/bench_r2_8gpu.err
-echo "bench rc $?"; tail -3 gpurun_out/bench_r2_8gpu.err | cut -c1-300
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_r2_8gpu.json').read().strip().splitlines()[-1])
-print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e'],'parity',d.get('sharded_parity'),'strong',d.get('strong'))
-print(d['config']['host_pinning'], d['clocks'])
-PY
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_detection.py tests/test_gpu_full_size.py -x -q -m gpu > gpurun_out/g_tests.log 2>&1
+echo "rc $?" >> gpurun_out/g_tests.log
+tail -3 gpurun_out/g_tests.log
+for v in "" r1 r2 m3 l8; do
+  echo "== variant $v"
+  if [ -n "$v" ]; then export TF_LIB_PATH=$PWD/profiles/tools/_var/libtf_$v.so; fi
+  python profiles/tools/gather_time.py 2>&1 | grep "nans=True"
+done
+unset TF_LIB_PATH
+echo "== general"
+TF_GATHER_GENERAL=1 TF_SOBEL_GENERAL=1 python profiles/tools/gather_time.py 2>&1 | grep "nans=True"

@@ -412,6 +412,33 @@ def test_sobel_around_nan_inf_and_wild_flow():
     assert np.max(np.abs(got[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1.0)) < 1e-12
 
 
+def test_diff_and_default_convolve_around_nan_inf_and_wild_flow():
+    """The lean diff / cross-7 kernels and their out-of-line general path (image border, first / last frame, samples
+    outside the image, NaN / huge flow vectors, quantised positions on the half-way points): bit-exact with the oracle."""
+    import tobac_flow_b200 as tfb
+    bt = synthetic.bt_sequence(6, 203, 331, seed=78, nans=True)
+    bt[3, 120, 200] = np.inf
+    bt[4] = np.nan
+    rng = np.random.default_rng(6)
+    fwd = (rng.standard_normal(bt.shape + (2,)) * 1.5).astype(np.float32)
+    bwd = (rng.standard_normal(bt.shape + (2,)) * 1.5).astype(np.float32)
+    fwd[1, 10, 10] = np.nan
+    bwd[1, 20, 20] = 1e9
+    bwd[2, 30, 30] = -1e9
+    fwd[2, 40, 40] = np.inf
+    fwd[0, :, :5] = 30.0
+    bwd[3, -4:, :] = 7.0                      # off the bottom edge
+    fwd[3, 60:90, 60:90] = (np.arange(30, dtype=np.float32)[None, :, None] + 0.5) / 32   # exact ties of the 1/32 grid
+    bwd[5, :, :] = np.float32(1.0) / 64
+    flow = tfb.Flow(fwd, bwd)
+    backend = "cv2" if ops.have_cv2() else "numpy"
+    with np.errstate(all="ignore"):
+        assert_same(flow.diff(bt), ops.diff(bt, fwd, bwd, backend=backend))
+        assert_same(flow.convolve(bt), ops.convolve(bt, fwd, bwd, backend=backend))
+        # non-default fill value (the same-step taps outside the image take it)
+        assert_same(flow.convolve(bt, fill_value=-3.5), ops.convolve(bt, fwd, bwd, fill_value=-3.5, backend=backend))
+
+
 def test_float64_frames_are_normalised_in_float64():
     """float64 (and integer) frames: numpy keeps / promotes the dtype, so the reference quantises them in float64; the
     u8 pair must match that bit for bit (casting to float32 first moves a few per cent of the pixels by one count)."""

@@ -8,6 +8,8 @@
 //
 // One thread per output pixel; the tap stack lives in registers only.  HBM traffic per pixel-step: 3 operand frames
 // (neighbour re-reads hit L1/L2), 2 flow fields (16 B) and the result.
+#include <stdlib.h>
+
 #include <mutex>
 #include <type_traits>
 
@@ -43,6 +45,14 @@ __device__ __forceinline__ int cv_round_dev(float v) {
     return __float2int_rn(v);
 }
 __device__ __forceinline__ int sat_short(int v) { return min(max(v, -32768), 32767); }
+
+// rint(32 p) without the conversion unit: 32 p is exact in fp32, so the single rounding of fma(p, 32, 1.5 * 2^23) IS
+// cvRound's round-half-even, and the integer sits in the low mantissa bits.  Exact for |32 p| < 2^22; outside that range
+// (and for NaN / infinities) the returned value is negative or >= 2^22, i.e. it fails every "footprint inside the image"
+// test below (images are at most 32767 wide: cv2.remap's short coordinates), and the caller takes the general path.
+constexpr float kQMagic = 12582912.f;
+constexpr int kQMagicBits = 0x4B400000;
+__device__ __forceinline__ int quantise_fast(float p) { return __float_as_int(fmaf(p, 32.f, kQMagic)) - kQMagicBits; }
 
 // a source image that may be a real frame or the virtual all-`fill` frame of convolve.py:307-314
 template <typename T>
@@ -87,6 +97,18 @@ __device__ __forceinline__ T remap_at(const Src& s, float px, float py) {
         if ((unsigned)ix < (unsigned)W && (unsigned)iy < (unsigned)H) return s.at(iy, ix);
         return s.fill;
     } else {
+        if constexpr (INTERP == TF_LINEAR) {
+            // the 2 x 2 footprint inside the image (almost every sample): no float -> int conversions, one range test per axis
+            const int qx = quantise_fast(px), qy = quantise_fast(py);
+            if ((unsigned)qx < (unsigned)(min(max(W - 1, 0), 32767) << 5) && (unsigned)qy < (unsigned)(min(max(H - 1, 0), 32767) << 5)) {
+                const int ix = qx >> 5, iy = qy >> 5;
+                const float fx = (float)(qx & 31) * (1.0f / 32.0f), fy = (float)(qy & 31) * (1.0f / 32.0f);
+                const float wx0 = 1.f - fx, wy0 = 1.f - fy;  // exact
+                const T w00 = (T)(wy0 * wx0), w01 = (T)(wy0 * fx), w10 = (T)(fy * wx0), w11 = (T)(fy * fx);  // exact
+                const T v00 = s.at(iy, ix), v01 = s.at(iy, ix + 1), v10 = s.at(iy + 1, ix), v11 = s.at(iy + 1, ix + 1);
+                return add_rn(add_rn(add_rn(mul_rn(v00, w00), mul_rn(v01, w01)), mul_rn(v10, w10)), mul_rn(v11, w11));
+            }
+        }
         const int sx = cv_round_dev(__fmul_rn(px, 32.f)), sy = cv_round_dev(__fmul_rn(py, 32.f));
         const int ix = sat_short(sx >> 5), iy = sat_short(sy >> 5);
         const int fxi = sx & 31, fyi = sy & 31;
@@ -94,18 +116,14 @@ __device__ __forceinline__ T remap_at(const Src& s, float px, float py) {
             const float fx = (float)fxi * (1.0f / 32.0f), fy = (float)fyi * (1.0f / 32.0f);
             const float wx0 = 1.f - fx, wy0 = 1.f - fy;  // exact
             const T w00 = (T)(wy0 * wx0), w01 = (T)(wy0 * fx), w10 = (T)(fy * wx0), w11 = (T)(fy * fx);  // exact
-            T v00, v01, v10, v11;
-            if ((unsigned)ix < (unsigned)max(W - 1, 0) && (unsigned)iy < (unsigned)max(H - 1, 0)) {
-                v00 = s.at(iy, ix); v01 = s.at(iy, ix + 1); v10 = s.at(iy + 1, ix); v11 = s.at(iy + 1, ix + 1);
-            } else {
-                if (ix >= W || ix + 1 < 0 || iy >= H || iy + 1 < 0) return s.fill;
-                const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
-                const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
-                v00 = (y0 && x0) ? s.at(iy, ix) : s.fill;
-                v01 = (y0 && x1) ? s.at(iy, ix + 1) : s.fill;
-                v10 = (y1 && x0) ? s.at(iy + 1, ix) : s.fill;
-                v11 = (y1 && x1) ? s.at(iy + 1, ix + 1) : s.fill;
-            }
+            // (footprints inside the image were taken above; this is the border form, valid for any position)
+            if (ix >= W || ix + 1 < 0 || iy >= H || iy + 1 < 0) return s.fill;
+            const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
+            const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
+            const T v00 = (y0 && x0) ? s.at(iy, ix) : s.fill;
+            const T v01 = (y0 && x1) ? s.at(iy, ix + 1) : s.fill;
+            const T v10 = (y1 && x0) ? s.at(iy + 1, ix) : s.fill;
+            const T v11 = (y1 && x1) ? s.at(iy + 1, ix + 1) : s.fill;
             return add_rn(add_rn(add_rn(mul_rn(v00, w00), mul_rn(v01, w01)), mul_rn(v10, w10)), mul_rn(v11, w11));
         } else if constexpr (INTERP == TF_LANCZOS4) {
             // remapLanczos4: 8 x 8 taps from (ix - 3, iy - 3); weights wy[k1] * wx[k2] (fp32 table product); inside: the
@@ -312,44 +330,57 @@ struct RedSobel {
     }
 };
 
-// Quantised cv2.remap position of one axis: integer part and 1/32 fraction index
-__device__ __forceinline__ void quantise_pos(float p, int& ip, int& fi) {
-    const int s = cv_round_dev(__fmul_rn(p, 32.f));
-    ip = sat_short(s >> 5);
-    fi = s & 31;
-}
-
 // All nine (dx, dy) in {-1,0,1}^2 taps of one warped slab at once (linear interpolation): when the nine sampling
 // positions quantise consistently (same fraction, integer parts one apart - the overwhelmingly common case) and the
 // 4x4 footprint is inside the image, load the 16 texels once and evaluate every tap from registers with exactly the
 // arithmetic of remap_at<TF_LINEAR>.  Returns false when the caller must fall back to per-tap sampling.
+// limit of the quantised centre position (minus one pixel) for which the 4 x 4 footprint lies inside an axis of n pixels
+__device__ __forceinline__ unsigned patch_limit(int n) { return (unsigned)(min(max(n - 3, 0), 32764) << 5); }
+
+// step 1: quantised positions of the three offsets per axis (p = fl32(fl32(flow + offset) + grid), convolve.py:56-63);
+// false unless they share the fraction, their integer parts are one apart and the 4 x 4 footprint is inside the image
+__device__ __forceinline__ bool patch9_locate(unsigned lim_x, unsigned lim_y, float2 f, int x, int y, int& qx, int& qy) {
+    const float xf = (float)x, yf = (float)y;
+    qx = quantise_fast(__fadd_rn(f.x, xf));
+    qy = quantise_fast(__fadd_rn(f.y, yf));
+    const int qxm = quantise_fast(__fadd_rn(__fadd_rn(f.x, -1.f), xf)), qxp = quantise_fast(__fadd_rn(__fadd_rn(f.x, 1.f), xf));
+    const int qym = quantise_fast(__fadd_rn(__fadd_rn(f.y, -1.f), yf)), qyp = quantise_fast(__fadd_rn(__fadd_rn(f.y, 1.f), yf));
+    return qxm + 32 == qx && qxp - 32 == qx && qym + 32 == qy && qyp - 32 == qy &&
+           (unsigned)(qx - 32) < lim_x && (unsigned)(qy - 32) < lim_y;
+}
+// step 2: the 16 texels
 template <typename T>
-__device__ __forceinline__ bool linear_patch9(const T* __restrict__ img, int H, int W, float2 f, int x, int y, T out[9]) {
-    int ix[3], iy[3], fx[3], fy[3];
+__device__ __forceinline__ void patch9_load(const T* __restrict__ img, int W, int qx, int qy, T p[4][4]) {
+    const T* row = img + (((qy >> 5) - 1) * W + ((qx >> 5) - 1));
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        quantise_pos(__fadd_rn(__fadd_rn(f.x, (float)(d - 1)), (float)x), ix[d], fx[d]);
-        quantise_pos(__fadd_rn(__fadd_rn(f.y, (float)(d - 1)), (float)y), iy[d], fy[d]);
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) p[r][c] = row[c];
+        row += W;
     }
-    const bool ok = fx[0] == fx[1] && fx[2] == fx[1] && fy[0] == fy[1] && fy[2] == fy[1] && ix[0] == ix[1] - 1 &&
-                    ix[2] == ix[1] + 1 && iy[0] == iy[1] - 1 && iy[2] == iy[1] + 1 && ix[0] >= 0 && ix[2] + 1 < W &&
-                    iy[0] >= 0 && iy[2] + 1 < H;
-    if (!ok) return false;
-    const float wfx = (float)fx[1] * (1.0f / 32.0f), wfy = (float)fy[1] * (1.0f / 32.0f);
+}
+// step 3: the nine taps, each with exactly the arithmetic of remap_at<TF_LINEAR>
+template <typename T>
+__device__ __forceinline__ void patch9_blend(const T p[4][4], int qx, int qy, T out[9]) {
+    const float wfx = (float)(qx & 31) * (1.0f / 32.0f), wfy = (float)(qy & 31) * (1.0f / 32.0f);
     const float wx0 = 1.f - wfx, wy0 = 1.f - wfy;
     const T w00 = (T)(wy0 * wx0), w01 = (T)(wy0 * wfx), w10 = (T)(wfy * wx0), w11 = (T)(wfy * wfx);
-    T p[4][4];
-    const T* base = img + iy[0] * W + ix[0];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) p[r][c] = base[r * W + c];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx)
             out[dy * 3 + dx] = add_rn(add_rn(add_rn(mul_rn(p[dy][dx], w00), mul_rn(p[dy][dx + 1], w01)),
                                              mul_rn(p[dy + 1][dx], w10)), mul_rn(p[dy + 1][dx + 1], w11));
+}
+
+template <typename T>
+__device__ __forceinline__ bool linear_patch9(const T* __restrict__ img, int W, unsigned lim_x, unsigned lim_y, float2 f, int x,
+                                              int y, T out[9]) {
+    int qx, qy;
+    if (!patch9_locate(lim_x, lim_y, f, x, y, qx, qy)) return false;
+    T p[4][4];
+    patch9_load<T>(img, W, qx, qy, p);
+    patch9_blend<T>(p, qx, qy, out);
     return true;
 }
 
@@ -364,12 +395,9 @@ constexpr unsigned SB_FULL = (1u << 27) - 1u;                                   
 #ifndef TF_GATHER_MINB
 #define TF_GATHER_MINB 4
 #endif
+// one output pixel (x, y) of frame t: every interpolation, reducer, dtype and border case
 template <typename SrcT, typename ST, int INTERP, int RC, unsigned SB>
-__global__ void __launch_bounds__(256, (RC == RC_SOBEL ? TF_GATHER_MINB : 1)) sl_gather_kernel(GatherArgs a) {
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    const int t = blockIdx.z;
-    if (x >= a.W || y >= a.H) return;
+__device__ __forceinline__ void gather_pixel(const GatherArgs& a, int x, int y, int t) {
     const int H = a.H, W = a.W;
     const long long hw = (long long)H * W;
     const int pix = y * W + x;
@@ -424,7 +452,7 @@ __global__ void __launch_bounds__(256, (RC == RC_SOBEL ? TF_GATHER_MINB : 1)) sl
         } else {
             bool have_patch = false;
             if constexpr (INTERP == TF_LINEAR && !std::is_same<SrcT, int>::value) {
-                if (bits == 0x1ffu && src.p != nullptr) have_patch = linear_patch9<SrcT>(src.p, H, W, f, x, y, tapv);
+                if (bits == 0x1ffu && src.p != nullptr) have_patch = linear_patch9<SrcT>(src.p, W, patch_limit(W), patch_limit(H), f, x, y, tapv);
             }
             if (!have_patch) {
 #pragma unroll
@@ -460,6 +488,249 @@ __global__ void __launch_bounds__(256, (RC == RC_SOBEL ? TF_GATHER_MINB : 1)) sl
     }
 }
 
+template <typename SrcT, typename ST, int INTERP, int RC, unsigned SB>
+__global__ void __launch_bounds__(256, (RC == RC_SOBEL ? TF_GATHER_MINB : 1)) sl_gather_kernel(GatherArgs a) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= a.W || y >= a.H) return;
+    gather_pixel<SrcT, ST, INTERP, RC, SB>(a, x, y, blockIdx.z);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Lean kernels for the two other operators the reference runs on every frame: Flow.diff (flow.py:182-186; taps t-1, t, t+1
+// at the centre, RedDiff) and Flow.convolve with its default structure (generate_binary_structure(3, 1), func = None:
+// the seven taps stacked), fp32, linear interpolation.  The 27-tap kernel above is bound by its two dependent memory
+// round trips (flow, then texels; ncu: 11-18 long-scoreboard stalls per issue at 39-41 % of the DRAM bandwidth).  Here a
+// thread walks LEAN_ROWS rows (8 apart, so that the CTA's warps stay on adjacent rows) and requests the flow vectors of
+// its next row before it samples the current one: one exposed round trip per pixel.  Samples whose 2 x 2 footprint is
+// not inside the image, and the first / last frame of a series, go through gather_pixel (out of line).
+// ------------------------------------------------------------------------------------------------------------------
+template <typename SrcT, typename ST, int INTERP, int RC, unsigned SB>
+__device__ __noinline__ void gather_pixel_call(const void* cur0, const float2* fflow0, const float2* bflow0, void* out,
+                                               long long out_tap_stride, int n_frames, int has_prev, int has_next, int H,
+                                               int W, int reducer, double fill, int x, int y, int t) {
+    GatherArgs a;
+    a.cur0 = cur0; a.fflow0 = fflow0; a.bflow0 = bflow0; a.out = out; a.out_tap_stride = out_tap_stride;
+    a.n_frames = n_frames; a.has_prev = has_prev; a.has_next = has_next; a.H = H; a.W = W; a.structure = SB;
+    a.reducer = reducer; a.fill = fill;
+    gather_pixel<SrcT, ST, INTERP, RC, SB>(a, x, y, t);
+}
+
+// one bilinear sample whose footprint is known to be inside the image: remap_at<TF_LINEAR>'s arithmetic
+__device__ __forceinline__ float lean_sample(const float* __restrict__ img, int W, int qx, int qy) {
+    const float* p = img + ((qy >> 5) * W + (qx >> 5));
+    const float v00 = __ldg(p), v01 = __ldg(p + 1), v10 = __ldg(p + W), v11 = __ldg(p + W + 1);
+    const float fx = (float)(qx & 31) * (1.0f / 32.0f), fy = (float)(qy & 31) * (1.0f / 32.0f);
+    const float wx0 = 1.f - fx, wy0 = 1.f - fy;
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00, wy0 * wx0), __fmul_rn(v01, wy0 * fx)), __fmul_rn(v10, fy * wx0)),
+                     __fmul_rn(v11, fy * fx));
+}
+
+constexpr int LEAN_ROWS = 4;
+enum { LEAN_DIFF = 0, LEAN_CROSS7 = 1 };
+
+// (measured, ms per 24 CONUS frames: diff 0.558 at 8 CTAs per SM / 0.591 at 6; cross-7 1.058 / 0.953; 27-tap kernel 0.879 / 1.277)
+template <int MODE>
+__global__ void __launch_bounds__(256, MODE == LEAN_DIFF ? 8 : 6) sl_lean_kernel(GatherArgs a) {
+    constexpr int RC = MODE == LEAN_DIFF ? RC_DIFF : RC_NONE;
+    constexpr unsigned SB = MODE == LEAN_DIFF ? SB_T3 : SB_CROSS7;
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int t = blockIdx.z;
+    const int H = a.H, W = a.W;
+    if (x >= W) return;
+    const long long hw = (long long)H * W;
+    const float* cur = reinterpret_cast<const float*>(a.cur0) + (long long)t * hw;
+    const float2* bfl = a.bflow0 + (long long)t * hw;
+    const float2* ffl = a.fflow0 + (long long)t * hw;
+    float* out = reinterpret_cast<float*>(a.out) + (long long)t * hw;
+    const bool series_inner = (t > 0 || a.has_prev) && (t < a.n_frames - 1 || a.has_next);
+    const unsigned lim_x = (unsigned)(min(max(W - 1, 0), 32767) << 5), lim_y = (unsigned)(min(max(H - 1, 0), 32767) << 5);
+    const float xf = (float)x;
+    int y = blockIdx.y * (8 * LEAN_ROWS) + threadIdx.y;
+    float2 bf_n = make_float2(0.f, 0.f), ff_n = bf_n;
+    if (y < H && series_inner) { bf_n = __ldg(bfl + y * W + x); ff_n = __ldg(ffl + y * W + x); }
+#pragma unroll 1
+    for (int k = 0; k < LEAN_ROWS && y < H; ++k, y += 8) {
+        const float2 bf = bf_n, ff = ff_n;
+        if (k + 1 < LEAN_ROWS && y + 8 < H && series_inner) { bf_n = __ldg(bfl + (y + 8) * W + x); ff_n = __ldg(ffl + (y + 8) * W + x); }
+        const int pix = y * W + x;
+        const float yf = (float)y;
+        // p = fl32(fl32(flow + 0) + grid) = fl32(flow + grid)   (convolve.py:56-63)
+        const int qx0 = quantise_fast(__fadd_rn(bf.x, xf)), qy0 = quantise_fast(__fadd_rn(bf.y, yf));
+        const int qx2 = quantise_fast(__fadd_rn(ff.x, xf)), qy2 = quantise_fast(__fadd_rn(ff.y, yf));
+        bool fast = series_inner && (unsigned)qx0 < lim_x && (unsigned)qy0 < lim_y && (unsigned)qx2 < lim_x && (unsigned)qy2 < lim_y;
+        if (MODE == LEAN_CROSS7) fast = fast && x >= 1 && x < W - 1 && y >= 1 && y < H - 1;
+        if (fast) {
+            const float v0 = lean_sample(cur - hw, W, qx0, qy0);
+            const float v2 = lean_sample(cur + hw, W, qx2, qy2);
+            const float c = __ldg(cur + pix);
+            if (MODE == LEAN_DIFF) {
+                RedDiff<float> rd;
+                rd.x[0] = v0; rd.x[1] = c; rd.x[2] = v2;
+                float r = rd.finish();
+                if (c != c) r = (float)a.fill;            // res[np.isnan(data)] = fill_value   (convolve.py:346-347)
+                out[pix] = r;
+            } else {
+                const long long ts = a.out_tap_stride;
+                float* o = out + pix;
+                o[0] = v0;
+                o[ts] = __ldg(cur + pix - W);
+                o[2 * ts] = __ldg(cur + pix - 1);
+                o[3 * ts] = c;
+                o[4 * ts] = __ldg(cur + pix + 1);
+                o[5 * ts] = __ldg(cur + pix + W);
+                o[6 * ts] = v2;
+            }
+        } else {
+            gather_pixel_call<float, float, TF_LINEAR, RC, SB>(a.cur0, a.fflow0, a.bflow0, a.out, a.out_tap_stride, a.n_frames,
+                                                               a.has_prev, a.has_next, H, W, a.reducer, a.fill, x, y, t);
+        }
+    }
+}
+
+template <int MODE>
+static int launch_lean(const GatherArgs& a, cudaStream_t s) {
+    const double per_px = 3.0 * 4 + 16.0 + (MODE == LEAN_DIFF ? 4.0 : 28.0);
+    LaunchTimer lt(KC_GATHER, per_px * a.H * a.W * a.n_frames, s, cdiv(a.n_frames, 65535));
+    const long long hw = (long long)a.H * a.W;
+    for (int t0 = 0; t0 < a.n_frames; t0 += 65535) {
+        GatherArgs b = a;
+        const int nt = min(a.n_frames - t0, 65535);
+        b.cur0 = reinterpret_cast<const float*>(a.cur0) + t0 * hw;
+        b.fflow0 = a.fflow0 + t0 * hw;
+        b.bflow0 = a.bflow0 + t0 * hw;
+        b.out = reinterpret_cast<float*>(a.out) + t0 * hw;
+        b.n_frames = nt;
+        b.has_prev = (t0 > 0) ? 1 : a.has_prev;
+        b.has_next = (t0 + nt < a.n_frames) ? 1 : a.has_next;
+        sl_lean_kernel<MODE><<<dim3(cdiv(a.W, 32), cdiv(a.H, 8 * LEAN_ROWS), nt), dim3(32, 8), 0, s>>>(b);
+    }
+    return check_launch("tf_sl_convolve (lean)");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Flow.sobel as the reference calls it (fp32 frames, fp64 stack, linear interpolation, plain direction; sobel.py:7-86
+// through flow.py:160-180): the 27-tap kernel above spends 830 instructions per pixel, most of them on cases this call
+// never meets.  Here a pixel whose three 3 x 3 slabs lie inside the series and the image
+//   * quantises the warped positions without conversions (quantise_fast) and blends each warped slab from its 4 x 4 patch,
+//   * reduces slab by slab: the separable (1,2,1) x (1,2,1) x (-1,0,1) sums of a slab are folded into the three gradient
+//     accumulators as soon as its nine taps exist, in exactly the order RedSobel::separable adds them (bit-identical
+//     results), so only nine taps are live at a time;
+//   * handles NaN taps per slab (a slab's all-positive sum is finite iff its taps are): NaN -> the centre value, as nansum
+//     of (tap - centre) does; infinities and everything at the image / series border go to gather_pixel.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sobel_slab_sums(const float v[9], double& gxs, double& gys, double& gts) {
+    double rd[3], rs[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double p = (double)v[3 * r], q = (double)v[3 * r + 1], s = (double)v[3 * r + 2];
+        rd[r] = s - p;
+        rs[r] = (p + s) + 2.0 * q;
+    }
+    gxs = (rd[0] + rd[2]) + 2.0 * rd[1];
+    gys = rs[2] - rs[0];
+    gts = (rs[0] + rs[2]) + 2.0 * rs[1];
+}
+
+// NaN taps of a slab -> the centre value; false when a tap is infinite (general form needed)
+__device__ __forceinline__ bool sobel_patch_nans(float v[9], float centre, int skip) {
+    bool inf = false;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        if (k == skip) continue;
+        inf |= fabsf(v[k]) == INFINITY;
+        v[k] = v[k] != v[k] ? centre : v[k];
+    }
+    return !inf;
+}
+
+#ifndef TF_SOBEL_MINB
+#define TF_SOBEL_MINB 4
+#endif
+// rows per thread: 1 (measured, ms per 24 CONUS frames: 2.07 with one row, 2.32-2.35 with 2 or 4 rows and the next row's
+// flow vectors requested ahead -- the loop-carried state spills at 64 registers, and 80 registers cost a CTA per SM)
+#ifndef TF_SOBEL_ROWS
+#define TF_SOBEL_ROWS 1
+#endif
+__global__ void __launch_bounds__(256, TF_SOBEL_MINB) sobel_lin_f64_kernel(GatherArgs a) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int t = blockIdx.z;
+    const int H = a.H, W = a.W;
+    if (x >= W) return;
+    const long long hw = (long long)H * W;
+    const float* cur = reinterpret_cast<const float*>(a.cur0) + (long long)t * hw;
+    const float2* bfl = a.bflow0 + (long long)t * hw;
+    const float2* ffl = a.fflow0 + (long long)t * hw;
+    const bool inner_xt = x >= 1 && x < W - 1 && (t > 0 || a.has_prev) && (t < a.n_frames - 1 || a.has_next);
+    const unsigned lim_x = patch_limit(W), lim_y = patch_limit(H);
+    // a thread walks TF_SOBEL_ROWS rows, 8 apart, and requests the flow vectors of its next row before it works on the
+    // current one (they are the head of the pixel's dependent load chain)
+    int y = blockIdx.y * (8 * TF_SOBEL_ROWS) + threadIdx.y;
+    float2 bf_n = make_float2(0.f, 0.f), ff_n = bf_n;
+    if (y < H && inner_xt) { bf_n = __ldg(bfl + y * W + x); ff_n = __ldg(ffl + y * W + x); }
+#pragma unroll 1
+    for (int k = 0; k < TF_SOBEL_ROWS && y < H; ++k, y += 8) {
+    const float2 bf = bf_n, ff = ff_n;
+    if (k + 1 < TF_SOBEL_ROWS && y + 8 < H && inner_xt) { bf_n = __ldg(bfl + (y + 8) * W + x); ff_n = __ldg(ffl + (y + 8) * W + x); }
+    const int pix = y * W + x;
+    double* out = reinterpret_cast<double*>(a.out) + (long long)t * hw + pix;
+    const bool inner = inner_xt && y >= 1 && y < H - 1;
+    bool done = false;
+    if (inner) {
+        float v[9];
+        const float* c0 = cur + pix - W - 1;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) v[j] = c0[(j / 3) * W + (j % 3)];
+        const float centre = v[4];
+        if (centre != centre) {                  // res[np.isnan(data)] = fill_value   (convolve.py:346-347)
+            *out = a.fill;
+            continue;
+        }
+        // both warped patches are located and requested before anything is reduced: two dependent memory round trips per
+        // pixel (flow, then texels) instead of three -- the kernel is bound by that latency chain, not by instruction issue
+        int qx0, qy0, qx2, qy2;
+        bool ok = fabsf(centre) != INFINITY;
+        ok = patch9_locate(lim_x, lim_y, bf, x, y, qx0, qy0) && ok;
+        ok = patch9_locate(lim_x, lim_y, ff, x, y, qx2, qy2) && ok;
+        if (ok) {
+            float p0[4][4], p2[4][4];
+            patch9_load<float>(cur - hw, W, qx0, qy0, p0);
+            patch9_load<float>(cur + hw, W, qx2, qy2, p2);
+            double gx1, gy1, gt1;
+            sobel_slab_sums(v, gx1, gy1, gt1);
+            // the centre tap has no weight in any gradient: gx1 and gy1 together cover the other eight taps
+            if (!(isfinite(gx1) && isfinite(gy1))) {
+                ok = sobel_patch_nans(v, centre, 4);
+                sobel_slab_sums(v, gx1, gy1, gt1);
+            }
+            double gx0, gy0, gt0, gx2, gy2, gt2;
+            patch9_blend<float>(p0, qx0, qy0, v);
+            sobel_slab_sums(v, gx0, gy0, gt0);
+            if (!isfinite(gt0)) {
+                ok = sobel_patch_nans(v, centre, -1) && ok;
+                sobel_slab_sums(v, gx0, gy0, gt0);
+            }
+            patch9_blend<float>(p2, qx2, qy2, v);
+            sobel_slab_sums(v, gx2, gy2, gt2);
+            if (!isfinite(gt2)) {
+                ok = sobel_patch_nans(v, centre, -1) && ok;
+                sobel_slab_sums(v, gx2, gy2, gt2);
+            }
+            if (ok) {
+                const double gx = (gx0 + gx2) + 2.0 * gx1;
+                const double gy = (gy0 + gy2) + 2.0 * gy1;
+                const double gt = gt2 - gt0;
+                *out = sqrt(gx * gx + gy * gy + gt * gt);
+                done = true;
+            }
+        }
+    }
+    if (!done)
+        gather_pixel_call<float, double, TF_LINEAR, RC_SOBEL, SB_FULL>(a.cur0, a.fflow0, a.bflow0, a.out, a.out_tap_stride, a.n_frames,
+                                                                       a.has_prev, a.has_next, H, W, a.reducer, a.fill, x, y, t);
+    }
+}
+
 static thread_local double g_gather_bytes = 0;
 
 template <typename SrcT, typename ST, int INTERP, int RC, unsigned SB = 0u>
@@ -487,6 +758,24 @@ static int launch_gather(const GatherArgs& a, cudaStream_t s) {
         sl_gather_kernel<SrcT, ST, INTERP, RC, SB><<<grid, block, 0, s>>>(b);
     }
     return check_launch("tf_sl_convolve");
+}
+
+static int launch_sobel_fast(const GatherArgs& a, cudaStream_t s) {
+    LaunchTimer lt(KC_GATHER, (3.0 * 4 + 16.0 + 8.0) * a.H * a.W * a.n_frames, s, cdiv(a.n_frames, 65535));
+    const long long hw = (long long)a.H * a.W;
+    for (int t0 = 0; t0 < a.n_frames; t0 += 65535) {
+        GatherArgs b = a;
+        const int nt = min(a.n_frames - t0, 65535);
+        b.cur0 = reinterpret_cast<const float*>(a.cur0) + t0 * hw;
+        b.fflow0 = a.fflow0 + t0 * hw;
+        b.bflow0 = a.bflow0 + t0 * hw;
+        b.out = reinterpret_cast<double*>(a.out) + t0 * hw;
+        b.n_frames = nt;
+        b.has_prev = (t0 > 0) ? 1 : a.has_prev;
+        b.has_next = (t0 + nt < a.n_frames) ? 1 : a.has_next;
+        sobel_lin_f64_kernel<<<dim3(cdiv(a.W, 32), cdiv(a.H, 8 * TF_SOBEL_ROWS), nt), dim3(32, 8), 0, s>>>(b);
+    }
+    return check_launch("tf_sl_convolve (sobel)");
 }
 
 template <typename SrcT, typename ST, int INTERP>
@@ -645,10 +934,15 @@ extern "C" int tf_sl_convolve(const void* cur0, int n_frames, int has_prev, int 
     const unsigned sb = a.structure;
     const bool f32 = src_dtype == TF_F32, f64s = src_dtype == TF_F64, st32 = stack_dtype == TF_F32, st64 = stack_dtype == TF_F64;
     if (interp == TF_LINEAR) {
+        static const bool lean_off = getenv("TF_GATHER_GENERAL") != nullptr;       // A/B: the 27-tap kernel for diff / cross-7
+        if (f32 && st32 && rc == RC_DIFF && sb == SB_T3 && !lean_off) return launch_lean<LEAN_DIFF>(a, s);
+        if (f32 && st32 && rc == RC_NONE && sb == SB_CROSS7 && !lean_off) return launch_lean<LEAN_CROSS7>(a, s);
         if (f32 && st32 && rc == RC_DIFF && sb == SB_T3) return launch_gather<float, float, TF_LINEAR, RC_DIFF, SB_T3>(a, s);
         if (f32 && st32 && rc == RC_STAT && sb == SB_T3) return launch_gather<float, float, TF_LINEAR, RC_STAT, SB_T3>(a, s);
         if (f64s && st32 && rc == RC_STAT && sb == SB_T3) return launch_gather<double, float, TF_LINEAR, RC_STAT, SB_T3>(a, s);
         if (f32 && st32 && rc == RC_STAT && sb == SB_S5) return launch_gather<float, float, TF_LINEAR, RC_STAT, SB_S5>(a, s);
+        static const bool sobel_general = getenv("TF_SOBEL_GENERAL") != nullptr;   // A/B: the 27-tap kernel for every pixel
+        if (f32 && st64 && reducer == TF_RED_SOBEL && sb == SB_FULL && !sobel_general) return launch_sobel_fast(a, s);
         if (f32 && st64 && rc == RC_SOBEL && sb == SB_FULL) return launch_gather<float, double, TF_LINEAR, RC_SOBEL, SB_FULL>(a, s);
         if (f32 && st32 && rc == RC_SOBEL && sb == SB_FULL) return launch_gather<float, float, TF_LINEAR, RC_SOBEL, SB_FULL>(a, s);
         if (f32 && st32 && rc == RC_NONE && sb == SB_CROSS7) return launch_gather<float, float, TF_LINEAR, RC_NONE, SB_CROSS7>(a, s);
