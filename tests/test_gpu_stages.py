@@ -1,8 +1,9 @@
 """GPU stage parity: the Farneback pipeline stage by stage (through the C ABI) against the oracle's restatement of
 OpenCV's optflowgf.cpp (oracle/farneback_np.py, itself pinned to cv2 in tests/test_oracle_farneback.py).
 
-Level images: the fused tile kernels must give the same bits as the separable two-pass kernels and agree with the
-oracle to a few ulp of the 0..255 range (fp32 sums in the same order, FMA contraction aside).  Polynomial expansion:
+Level images: the one-pass kernels (row kernel with combined blur x resize taps for W % 4 == 0, tile kernels otherwise)
+agree with the separable two-pass kernels and with the oracle to a few ulp of the 0..255 range (fp32 sums; the tile
+kernels add in the two-pass order and give the same bits, the row kernel associates differently).  Polynomial expansion:
 fp32 horizontal sums where OpenCV uses fp64 accumulators, so a relative tolerance (2e-5 of the channel's range).
 """
 import numpy as np
@@ -34,7 +35,10 @@ def test_pyramid_levels_fused_vs_two_pass_vs_oracle(H, W):
         fused = tflow.fb_pyramid_level(q0, q1, li)
         two = tflow.fb_pyramid_level(q0, q1, li, two_pass=True)
         assert fused.shape == (2, lvl["h"], lvl["w"])
-        assert np.array_equal(fused, two), (li, np.abs(fused - two).max())
+        if W % 4 == 0:
+            assert np.abs(fused - two).max() <= 2e-4, (li, np.abs(fused - two).max())
+        else:
+            assert np.array_equal(fused, two), (li, np.abs(fused - two).max())
         if H * W <= 400 * 700:      # the numpy oracle is slow on big frames
             for k, q in enumerate((q0, q1)):
                 ref = farneback_np.pyramid_level(q, lvl)

@@ -398,6 +398,111 @@ __global__ void __launch_bounds__(256, 6) blur_resize_tile_kernel(const uint8_t*
     }
 }
 
+// Down-sampled level, one CTA per destination row (the default for W % 4 == 0).
+// Blur followed by bilinear resize is one separable filter per destination pixel: with y0 / y0 + 1 the two source rows of
+// destination row j and fy the weight of the second,
+//     (1 - fy) * sum_k g[k] S(y0 - r + k) + fy * sum_k g[k] S(y0 + 1 - r + k) = sum_{c = 0 .. ksize} cw[c] S(y0 - r + c),
+//     cw[c] = g[c] + fy * (g[c - 1] - g[c])          (g[-1] = g[ksize] = 0)
+// and the same along x.  So a destination row needs ONE vertical pass over ksize + 1 image rows (not two blurred rows),
+// and a destination pixel ONE horizontal pass over ksize + 1 vertical sums (not four blurred values):
+//   1. vertical: the CTA forms the W vertical sums of its row, a thread eight columns at a time (two 32-bit words of four
+//      pixels, packed fp32 conversions and multiply-adds), into shared memory;
+//   2. horizontal: a thread per destination pixel walks its ksize + 1 sums with its own combined taps.
+// No halo, no intermediate rows in HBM, about half the multiply-adds of blurring both source rows / columns, and the
+// image rows are read straight from L2 (neighbouring destination rows share 60 % of them).  fp32 sums in a different
+// association than the two-pass kernels: the level images agree to ~1e-5 of the 0..255 range (tests/test_gpu_stages.py).
+struct RowTaps {
+    int ksize;
+    float g[kMaxBlurTaps + 1];    // g[ksize] = 0
+    float dg[kMaxBlurTaps + 1];   // dg[c] = g[c - 1] - g[c]
+};
+
+__device__ __forceinline__ float2 bytes_to_float2(unsigned v, unsigned sel_lo, unsigned sel_hi) {
+    const float2 m = make_float2(__uint_as_float(__byte_perm(v, 0x4B000000u, sel_lo)),
+                                 __uint_as_float(__byte_perm(v, 0x4B000000u, sel_hi)));
+    return __fadd2_rn(m, make_float2(-8388608.f, -8388608.f));
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) pyr_row_kernel(const uint8_t* __restrict__ q0, const uint8_t* __restrict__ q1,
+                                                     float* __restrict__ out, int H, int W, int h, int w, double scale_x,
+                                                     double scale_y, RowTaps taps) {
+    extern __shared__ __align__(16) float pr_smem[];
+    float* V = pr_smem;                                          // skew32(W) vertical sums of this destination row
+    __shared__ float s_cv[kMaxBlurTaps + 1], s_g[kMaxBlurTaps + 1], s_dg[kMaxBlurTaps + 1];
+    __shared__ int s_row[kMaxBlurTaps + 1];
+    const int tid = threadIdx.x;
+    const int j = blockIdx.x, img = blockIdx.y;
+    const int ksize = taps.ksize, rad = ksize >> 1;
+    const uint8_t* src = ((img & 1) ? q1 : q0) + (long long)(img >> 1) * H * W;
+    int y0, y1; float fy;
+    resize_coord(j, scale_y, H, y0, y1, fy);
+    const int ys = y0 - rad;
+    for (int c = tid; c <= ksize; c += NT) {
+        const float g = taps.g[c], dg = taps.dg[c];
+        s_g[c] = g; s_dg[c] = dg;
+        s_cv[c] = fmaf(fy, dg, g);
+        s_row[c] = reflect101(ys + c, H);
+    }
+    __syncthreads();
+    const bool rows_inside = ys >= 0 && ys + ksize < H;
+    const int W4 = W >> 2;
+    const unsigned* src32 = reinterpret_cast<const unsigned*>(src);
+
+    // 1. vertical
+    for (int cg0 = tid; cg0 < W4; cg0 += 2 * NT) {
+        const bool has1 = cg0 + NT < W4;
+        float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+        if (rows_inside) {
+            const unsigned* p = src32 + (long long)ys * W4 + cg0;
+#pragma unroll 6
+            for (int r = 0; r <= ksize; ++r) {
+                const float2 wr = make_float2(s_cv[r], s_cv[r]);
+                const unsigned u = __ldg(p), v = has1 ? __ldg(p + NT) : 0u;
+                p += W4;
+                a0 = __ffma2_rn(wr, bytes_to_float2(u, 0x7540u, 0x7541u), a0);
+                a1 = __ffma2_rn(wr, bytes_to_float2(u, 0x7542u, 0x7543u), a1);
+                b0 = __ffma2_rn(wr, bytes_to_float2(v, 0x7540u, 0x7541u), b0);
+                b1 = __ffma2_rn(wr, bytes_to_float2(v, 0x7542u, 0x7543u), b1);
+            }
+        } else {
+#pragma unroll 2
+            for (int r = 0; r <= ksize; ++r) {
+                const float2 wr = make_float2(s_cv[r], s_cv[r]);
+                const unsigned* p = src32 + (long long)s_row[r] * W4 + cg0;
+                const unsigned u = __ldg(p), v = has1 ? __ldg(p + NT) : 0u;
+                a0 = __ffma2_rn(wr, bytes_to_float2(u, 0x7540u, 0x7541u), a0);
+                a1 = __ffma2_rn(wr, bytes_to_float2(u, 0x7542u, 0x7543u), a1);
+                b0 = __ffma2_rn(wr, bytes_to_float2(v, 0x7540u, 0x7541u), b0);
+                b1 = __ffma2_rn(wr, bytes_to_float2(v, 0x7542u, 0x7543u), b1);
+            }
+        }
+        float* d = V + skew32(4 * cg0);
+        d[0] = a0.x; d[1] = a0.y; d[2] = a1.x; d[3] = a1.y;
+        if (has1) {
+            float* e = V + skew32(4 * (cg0 + NT));
+            e[0] = b0.x; e[1] = b0.y; e[2] = b1.x; e[3] = b1.y;
+        }
+    }
+    __syncthreads();
+
+    // 2. horizontal
+    float* orow = out + ((long long)img * h + j) * w;
+    for (int i = tid; i < w; i += NT) {
+        int x0, x1; float fx;
+        resize_coord(i, scale_x, W, x0, x1, fx);
+        const int xs = x0 - rad;
+        float acc = 0.f;
+        if (xs >= 0 && xs + ksize < W) {
+#pragma unroll 6
+            for (int c = 0; c <= ksize; ++c) acc = fmaf(fmaf(fx, s_dg[c], s_g[c]), V[skew32(xs + c)], acc);
+        } else {
+            for (int c = 0; c <= ksize; ++c) acc = fmaf(fmaf(fx, s_dg[c], s_g[c]), V[skew32(reflect101(xs + c, W))], acc);
+        }
+        orow[i] = acc;
+    }
+}
+
 // pass B at the full-resolution level (w == W, no resize), 4 outputs per thread (W % 4 == 0)
 __global__ void __launch_bounds__(256) blur_h4_fullres_kernel(const float* __restrict__ tmp, float* __restrict__ out, int W,
                                                               int h, BlurTaps taps) {
@@ -569,6 +674,43 @@ int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int 
     const int n_img = 2 * n_pairs;
     static const char* env_two_pass = getenv("TF_PYR_TWO_PASS");
     two_pass = two_pass || env_two_pass != nullptr;
+    static const char* env_tile = getenv("TF_PYR_TILE");     // A/B: the tile kernels instead of the row kernel
+    if (rp == 2 && !two_pass && env_tile == nullptr && (W & 3) == 0 && (((uintptr_t)q0 | (uintptr_t)q1) & 3) == 0 &&
+        ((long long)H * W & 3) == 0) {
+        RowTaps rt;
+        rt.ksize = ksize;
+        for (int c = 0; c <= ksize; ++c) {
+            const float gc = c < ksize ? taps.w[c] : 0.f, gm = c > 0 ? taps.w[c - 1] : 0.f;
+            rt.g[c] = gc;
+            rt.dg[c] = gm - gc;
+        }
+        for (int c = ksize + 1; c <= kMaxBlurTaps; ++c) rt.g[c] = rt.dg[c] = 0.f;
+        const int W4 = W >> 2;
+        const size_t smem = (size_t)(W + W / 32 + 8) * sizeof(float);
+        // threads: the W / 4 column words in an even number of rounds of two words per thread
+        const int rounds = cdiv(W4, 2 * 320);
+        const int nt_want = cdiv(cdiv(W4, 2 * rounds), 32) * 32;
+        const int n_launch = cdiv(n_img, 65534);
+        LaunchTimer lt(KC_PYRAMID, (2.0 * H * W + 8.0 * h * w) * n_pairs, s, n_launch);
+        for (int z0 = 0; z0 < n_img; z0 += 65534) {
+            const int nz = min(n_img - z0, 65534);
+            const uint8_t* a0 = q0 + (long long)(z0 / 2) * H * W;
+            const uint8_t* a1 = q1 + (long long)(z0 / 2) * H * W;
+            float* oz = out + (long long)z0 * h * w;
+            dim3 g(h, nz);
+#define TF_ROW_LAUNCH(NT_)                                                                                             \
+    do {                                                                                                               \
+        cudaFuncSetAttribute(pyr_row_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+        pyr_row_kernel<NT_><<<g, NT_, smem, s>>>(a0, a1, oz, H, W, h, w, sx, sy, rt);                                   \
+    } while (0)
+            if (nt_want <= 128) TF_ROW_LAUNCH(128);
+            else if (nt_want <= 192) TF_ROW_LAUNCH(192);
+            else if (nt_want <= 256) TF_ROW_LAUNCH(256);
+            else TF_ROW_LAUNCH(320);
+#undef TF_ROW_LAUNCH
+        }
+        return check_launch("pyramid level (row)");
+    }
     if (rp == 2 && !two_pass) {
         // one fused pass per down-sampled level; tile shape by down-sampling factor (bigger footprints, smaller tiles)
         const int n_launch = cdiv(n_img, 65534);
