@@ -522,30 +522,47 @@ def run_b200(args):
         torch.cuda.synchronize()
         host_np = host_in.numpy()
 
-        def e2e_step():
-            fl = tfb.create_flow(host_np)                  # H2D inside
-            d = fl.diff(host_np)                           # H2D + D2H inside
-            s = fl.sobel(host_np)
-            c = fl.convolve(host_np)
+        def e2e_step(stack_first=True):
+            fl = tfb.create_flow(host_np)                  # H2D inside; returns with the flow kernels queued
+            if stack_first:
+                c = fl.convolve(host_np)                   # D2H inside; the largest result first: it streams back while
+                s = fl.sobel(host_np)                      # the later pairs are still in the iteration kernels
+                d = fl.diff(host_np)
+            else:
+                d = fl.diff(host_np)
+                s = fl.sobel(host_np)
+                c = fl.convolve(host_np)
             return float(d[0, 0, 0]) + float(s[0, 0, 0]) + float(c[0, 0, 0, 0])
 
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        barrier()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        def e2e_time(stack_first):
+            e2e_step(stack_first)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                e2e_step(stack_first)
+            barrier()
+            dt = (time.perf_counter() - t0) / args.e2e_steps
+            if world > 1:
+                t = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return dt
+
+        dt_alt = e2e_time(False)
+        dt = e2e_time(True)
         e2e = {"value": Te * world / dt, "unit": UNIT, "h2d_bytes_per_step": Te * N * 4,
                "d2h_bytes_per_step": Te * N * (4 + 8 + 28), "frames_per_step": Te,
-               "note": "create_flow + diff + sobel + convolve via the numpy API; input pinned; create_flow uploads the "
-                       "frames once per step and the three operators reuse that device copy (operand cache keyed on the "
-                       "host buffer); every operator result is copied back to a host array inside the timed region; "
-                       "flows stay on the device (Flow keeps them resident)"}
+               "order": "create_flow, convolve, sobel, diff",
+               "value_diff_sobel_convolve_order": Te * world / dt_alt,
+               "note": "create_flow + convolve + sobel + diff via the numpy API; input pinned; create_flow uploads the "
+                       "frames once per step, queues the flow kernels batch by batch and returns; the three operators "
+                       "reuse the device copy of the frames (operand cache keyed on the host buffer) and start on the "
+                       "first frames while later pairs are still being computed (per-batch events, operator kernels on a "
+                       "high-priority stream); every operator result is copied back to a host array inside the timed "
+                       "region, and every call returns only when its result is complete on the host; flows stay on the "
+                       "device (Flow keeps them resident).  PCIe-bound: 150 MB of results per frame.  Calling the "
+                       "operator with the largest result first hides the flow computation behind its download; "
+                       "value_diff_sobel_convolve_order is the same step with the small results first"}
 
     # ---- extra (not the metric): the device-resident growth-marker detection on this rank's first frames ---------------
     detection = None

@@ -527,6 +527,33 @@ def test_host_results_beyond_the_pinned_cap(tfb, golden, monkeypatch):
     assert_same(got_c, want_c)
 
 
+def test_host_operators_overlapping_create_flow_equal_the_device_path(tfb, monkeypatch):
+    """create_flow on a long host array returns with its pair batches still queued (Flow._ready); the host operators
+    then run chunk by chunk on the operator stream behind the batch events.  Same bits as the device-tensor path, in
+    either call order, with small chunks so that many chunk / batch boundaries are crossed."""
+    import torch
+    from tobac_flow_b200 import flow as tflow
+    bt = synthetic.bt_sequence(45, 150, 202, seed=21, nans=True)
+    dev_t = torch.from_numpy(bt).cuda()
+    fd = tfb.create_flow(dev_t)
+    want_f, want_b = fd.forward_flow_device.cpu().numpy(), fd.backward_flow_device.cpu().numpy()
+    want = [x.cpu().numpy() for x in (fd.convolve(dev_t), fd.sobel(dev_t), fd.diff(dev_t))]
+    monkeypatch.setattr(tflow, "_HOST_CHUNK_BYTES", 3 * 150 * 202 * 4)
+    monkeypatch.setattr(tflow, "_HOST_PAIR_BATCH", 3)
+    for stack_first in (True, False):
+        tflow.operand_cache_clear()
+        fh = tfb.create_flow(bt)
+        assert fh._ready is not None and fh._ready[-1][0] == 45 and len(fh._ready) >= 4
+        if stack_first:
+            got = [fh.convolve(bt), fh.sobel(bt), fh.diff(bt)]
+        else:
+            got = [fh.diff(bt), fh.sobel(bt), fh.convolve(bt)][::-1]
+        for a, b in zip(got, want):
+            assert_same(a, b)
+        assert_same(fh.forward_flow, want_f)
+        assert_same(fh.backward_flow, want_b)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # lanczos interpolation (cv2.INTER_LANCZOS4; convolve.py:46-51): bit-exact against the oracle (itself bit-exact vs cv2)
 # ------------------------------------------------------------------------------------------------------------------

@@ -117,6 +117,30 @@ def _side_streams(dev):
     return _SIDE_STREAMS[key]
 
 
+_OP_STREAMS = {}
+
+
+def _operator_stream(dev):
+    """High-priority compute stream of a device: the operator kernels of a host call run here while the flow kernels of
+    the ``create_flow`` just before are still queued on the current stream (see ``Flow._ready``)."""
+    key = (dev.type, dev.index)
+    if key not in _OP_STREAMS:
+        _OP_STREAMS[key] = torch.cuda.Stream(dev, priority=-1)
+    return _OP_STREAMS[key]
+
+
+def _host_batch_plan(n_pairs: int, big: int):
+    """Pair batches of the host path: small first (the upload has only just started and the operators can begin on the
+    first frames), doubling up to the device path's batch size (full kernel efficiency once the data is there)."""
+    plan, b, left = [], _HOST_PAIR_BATCH, n_pairs
+    while left > 0:
+        n = min(b, left, big)
+        plan.append(n)
+        left -= n
+        b = min(2 * b, big)
+    return plan
+
+
 class _OperandCache:
     """Device copies of host operands, so that ``create_flow(bt)`` followed by ``flow.diff(bt)``, ``flow.sobel(bt)``,
     ``flow.convolve(bt)`` uploads ``bt`` once instead of four times.
@@ -391,6 +415,11 @@ class Flow:
         if forward_flow.shape[-1] != 2:
             raise ValueError("Flow vectors must have a size of 2 in the trailing dimension")
         self.shape = tuple(forward_flow.shape[:-1])
+        # [(frames_ready, event)]: set by create_flow on a host array.  The flow kernels are queued batch by batch on the
+        # current stream and create_flow returns without waiting for them; event k fires when flow vectors [0, frames_ready_k)
+        # are final.  Work queued on the current stream is ordered behind all of them anyway; the host operators use the
+        # events to start on the first frames (on the operator stream) while the later pairs are still being computed.
+        self._ready = None
         self._fwd_np = forward_flow if isinstance(forward_flow, np.ndarray) else None
         self._bwd_np = backward_flow if isinstance(backward_flow, np.ndarray) else None
         self._fwd_t = forward_flow if isinstance(forward_flow, torch.Tensor) else None
@@ -493,9 +522,26 @@ class Flow:
         chunks = [(a0, min(a0 + Tc, T)) for a0 in range(0, T, Tc)]
         cur = torch.cuda.current_stream()
         s_in, s_out = _side_streams(dev)
+        # Flow vectors still being computed (create_flow on a host array returned without waiting): the operator kernels go
+        # to the high-priority operator stream, each chunk behind the event of the pair batch that completes its frames,
+        # so results start to flow back over PCIe while the later pairs are in the iteration kernels.  Only taken when the
+        # operand is the resident copy that create_flow uploaded (its upload events are behind the same batch events).
+        ready = self._ready
+        if ready is not None and (resident is None or ready[-1][1].query()):
+            ready = None
+        s_k = _operator_stream(dev) if ready is not None else cur
+
+        def wait_flow(b0):
+            if ready is not None:
+                for upto, ev in ready:
+                    if upto >= b0:
+                        s_k.wait_event(ev)
+                        return
+                s_k.wait_event(ready[-1][1])
         # the operand buffer belongs to the upload stream's pool, so the copies need not wait for the work already queued
         # on the current stream (typically the flow kernels of the create_flow call just before): they run underneath it
-        s_out.wait_stream(cur)
+        if ready is None:
+            s_out.wait_stream(cur)
         ev_in = []
         if resident is not None:
             d_in = resident
@@ -511,18 +557,20 @@ class Flow:
         bufs, ev_free = [None, None], [None, None]
         for k, (a0, b0) in enumerate(chunks):
             if ev_in:
-                cur.wait_event(ev_in[min(k + 1, len(chunks) - 1)])  # this chunk and its right halo frame are here
+                s_k.wait_event(ev_in[min(k + 1, len(chunks) - 1)])  # this chunk and its right halo frame are here
+            wait_flow(b0)           # vectors of [a0, b0) final (the batch that made them also waited for frame b0's upload)
             slot = k & 1
             if ev_free[slot] is not None:
-                cur.wait_event(ev_free[slot])                       # the buffer's previous contents are on the host
+                s_k.wait_event(ev_free[slot])                       # the buffer's previous contents are on the host
             n = b0 - a0
             shape = (n_taps, n, H, W) if stack else (n, H, W)
-            if bufs[slot] is None or tuple(bufs[slot].shape) != shape:
-                bufs[slot] = torch.empty(shape, dtype=out_t, device=dev)
-            convolve_device(d_in[max(a0 - 1, 0):min(b0 + 1, T)], fwd[a0:b0], bwd[a0:b0], structure, method, fill_value,
-                            dtype, reducer, has_prev=a0 > 0, has_next=b0 < T, out=bufs[slot])
+            with torch.cuda.stream(s_k):
+                if bufs[slot] is None or tuple(bufs[slot].shape) != shape:
+                    bufs[slot] = torch.empty(shape, dtype=out_t, device=dev)
+                convolve_device(d_in[max(a0 - 1, 0):min(b0 + 1, T)], fwd[a0:b0], bwd[a0:b0], structure, method, fill_value,
+                                dtype, reducer, has_prev=a0 > 0, has_next=b0 < T, out=bufs[slot])
             ev_c = torch.cuda.Event()
-            ev_c.record(cur)
+            ev_c.record(s_k)
             s_out.wait_event(ev_c)
             if not pinned:
                 # flush the staging chunk this slot used two chunks ago into the pageable result (host-side copy)
@@ -552,6 +600,8 @@ class Flow:
                     pa, pb = pending[slot]
                     host[(slice(None), slice(pa, pb)) if stack else slice(pa, pb)] = stage[slot][(slice(None), slice(0, pb - pa)) if stack else slice(0, pb - pa)]
         cur.wait_stream(s_in)
+        if ready is not None:
+            cur.wait_stream(s_k)           # (the chunk buffers go back to the operator stream's pool behind its kernels)
         if resident is None:
             _OPERANDS.put(a, d_in)
         return host.numpy()
@@ -671,7 +721,7 @@ def _pair_batch(n_pairs: int, H: int, W: int, params, vr: bool = False) -> int:
 def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Tensor, smoothing_passes: int = 0,
                           interp_method: str = "linear", max_value: float | None = None,
                           next_frames: torch.Tensor | None = None, batch: int | None = None, vr_steps: int = 0,
-                          frames_ready: Callable | None = None) -> None:
+                          frames_ready: Callable | None = None, batch_plan=None, batch_done: Callable | None = None) -> None:
     """Fill ``fwd[i]`` and ``bwd[i + 1]`` for every consecutive pair of ``frames`` (device tensors, in place).
 
     ``frames`` (T, H, W) float32 or float64; ``fwd``/``bwd`` (>= T, H, W, 2) float32.  With ``next_frames`` the pairs are
@@ -688,6 +738,9 @@ def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Te
     fuse_clamp = (max_value is not None) and smoothing_passes == 0 and not use_vr
     params = _lib.default_params(max_value if fuse_clamp else 0.0)
     nb = batch or _pair_batch(n_pairs, H, W, params, use_vr)
+    if batch_plan is None:
+        batch_plan = [min(nb, n_pairs - p0) for p0 in range(0, n_pairs, nb)]
+    nb = max(batch_plan)
     # (measured: alternating consecutive pair batches between two streams, to fill the half-empty grids of the small
     # pyramid levels and the tail waves, gains nothing: 458-475 vs 460 ms per CONUS day)
     dev = frames.device
@@ -711,8 +764,8 @@ def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Te
     hw = H * W
     es = frames.element_size()
     st = _stream()
-    for p0 in range(0, n_pairs, nb):
-        n = min(nb, n_pairs - p0)
+    for bi, n in enumerate(batch_plan):
+        p0 = sum(batch_plan[:bi])
         if frames_ready is not None:
             frames_ready(p0 + n)          # make the stream wait until frames [0, p0 + n] have been uploaded
         f0 = frames.data_ptr() + p0 * hw * es
@@ -732,6 +785,8 @@ def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Te
                        "tf_smooth_flow_step")
             fwd[p0:p0 + n].copy_(tmp_f[:n])
             bwd[p0 + 1:p0 + 1 + n].copy_(tmp_b[:n])
+        if batch_done is not None:
+            batch_done(p0, n)
 
 
 def finalise_flow_device(fwd: torch.Tensor, bwd: torch.Tensor, max_value: float | None, clamp_all: bool,
@@ -755,6 +810,8 @@ def _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_meth
     _select_normalisation(normalisation_method)
     _interp_code(interp_method)
     frames_ready = batch = None
+    host_plan = False
+    ready = None
     host_a = None if isinstance(data, torch.Tensor) else _as_numpy(data)
     if host_a is not None and data_b is None and host_a.ndim == 3 and host_a.dtype == np.float32 and host_a.shape[0] > 2 * _HOST_PAIR_BATCH:
         # host input: upload in chunks on a side stream and start on the first pairs while the rest is in flight
@@ -772,7 +829,7 @@ def _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_meth
 
         def frames_ready(last_frame):
             torch.cuda.current_stream().wait_event(events[min(last_frame // _HOST_PAIR_BATCH, len(events) - 1)])
-        batch = _HOST_PAIR_BATCH
+        host_plan = True
         frames.record_stream(s_in)
         _OPERANDS.put(host_a if host_a.flags.c_contiguous else src.numpy(), frames)   # the operators reuse this copy
     else:
@@ -793,21 +850,46 @@ def _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_meth
     else:
         fwd = torch.full((T, H, W, 2), float("nan"), dtype=torch.float32, device=frames.device)
         bwd = torch.full((T, H, W, 2), float("nan"), dtype=torch.float32, device=frames.device)
+    early_final = False
     if frames_b is None:
+        plan = batch_done = None
+        if host_plan:
+            use_vr = bool(vr_steps) and vr_steps > 0
+            plan = _host_batch_plan(T - 1, _pair_batch(T - 1, H, W, _lib.default_params(0.0), use_vr))
+            if max_value is not None and max_value != 0 and smoothing_passes == 0 and not use_vr:
+                # the clamp is fused into the last iteration kernel, so a batch's vectors are final once the end rules of
+                # the first / last frame (flow.py:425-426) are applied: do that with the batch that computes them and mark
+                # every batch with an event (Flow._ready)
+                early_final, ready = True, []
+                fe = H * W * 2 * 4
+
+                def batch_done(p0, n):
+                    if p0 == 0:
+                        _lib.check(_lib.load().tf_flow_finalise(fwd.data_ptr(), bwd.data_ptr(), 1, H, W, 0.0, 0, 1, 0,
+                                                                _stream()), "tf_flow_finalise")
+                    last = p0 + n == T - 1
+                    if last:
+                        _lib.check(_lib.load().tf_flow_finalise(fwd.data_ptr() + (T - 1) * fe, bwd.data_ptr() + (T - 1) * fe, 1,
+                                                                H, W, 0.0, 0, 0, 1, _stream()), "tf_flow_finalise")
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream())
+                    # vectors of frames [0, p0 + n) are final: fwd[i] comes from pair i, bwd[i] from pair i - 1
+                    ready.append((T if last else p0 + n, ev))
         calculate_flow_device(frames, fwd, bwd, smoothing_passes, interp_method, max_value, vr_steps=vr_steps,
-                              batch=batch, frames_ready=frames_ready)
+                              batch=batch, frames_ready=frames_ready, batch_plan=plan, batch_done=batch_done)
     else:
         # calculate_flow_2 (flow.py:431-496): pairs (a[i], b[i]) for i < T-1
         calculate_flow_device(frames[:T - 1], fwd, bwd, smoothing_passes, interp_method, max_value,
                               next_frames=frames_b[:T - 1], vr_steps=vr_steps)
     clamp_all = max_value is not None and (smoothing_passes > 0 or (bool(vr_steps) and vr_steps > 0))
-    finalise_flow_device(fwd, bwd, max_value, clamp_all)
+    if not early_final:
+        finalise_flow_device(fwd, bwd, max_value, clamp_all)
     if max_value is not None and max_value == 0:
         # np.minimum(np.maximum(f, -0), 0) (flow.py:60-61): every finite vector becomes 0 (the kernels read a zero clamp
         # as "no clamp")
         fwd = torch.where(torch.isnan(fwd), fwd, torch.zeros_like(fwd))
         bwd = torch.where(torch.isnan(bwd), bwd, torch.zeros_like(bwd))
-    return fwd, bwd
+    return fwd, bwd, ready
 
 
 def calculate_flow(data, model: str = "Farneback", vr_steps: int = 0, smoothing_passes: int = 0,
@@ -815,8 +897,8 @@ def calculate_flow(data, model: str = "Farneback", vr_steps: int = 0, smoothing_
     """``calculate_flow`` (tobac_flow/flow.py:362-428): returns (forward_flow, backward_flow) numpy arrays."""
     if normalisation_kwargs:
         raise NotImplementedError("normalisation keyword arguments are not supported by the 'linear' method here")
-    fwd, bwd = _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_method,
-                                       normalisation_method, None)
+    fwd, bwd, _ = _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_method,
+                                          normalisation_method, None)
     return fwd.cpu().numpy(), bwd.cpu().numpy()
 
 
@@ -825,8 +907,8 @@ def calculate_flow_2(a, b, model: str = "Farneback", vr_steps: int = 0, smoothin
     """``calculate_flow_2`` (tobac_flow/flow.py:431-496)."""
     if normalisation_kwargs:
         raise NotImplementedError("normalisation keyword arguments are not supported by the 'linear' method here")
-    fwd, bwd = _calculate_flow_tensors(a, model, vr_steps, smoothing_passes, "linear", normalisation_method, None,
-                                       data_b=b)
+    fwd, bwd, _ = _calculate_flow_tensors(a, model, vr_steps, smoothing_passes, "linear", normalisation_method, None,
+                                          data_b=b)
     return fwd.cpu().numpy(), bwd.cpu().numpy()
 
 
@@ -836,8 +918,10 @@ def create_flow(data, model: str = "Farneback", vr_steps: int = 0, smoothing_pas
 
     The returned ``Flow`` keeps the vectors on the GPU.
     """
-    fwd, bwd = _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_method, "linear", max_value)
-    return Flow(fwd, bwd)
+    fwd, bwd, ready = _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_method, "linear", max_value)
+    flow = Flow(fwd, bwd)
+    flow._ready = ready
+    return flow
 
 
 def smooth_flow_step(forward_flow, backward_flow, method: str = "linear"):
