@@ -119,7 +119,10 @@ def measured_peak():
 # clocks
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    # One looping nvidia-smi, started BEFORE the warm-up steps: a fresh NVML client attaching to the device stalls kernel
+    # launches for some milliseconds, which showed up as 6-30 ms idle gaps inside the timed region when it was started
+    # there.  Only the samples taken between mark_begin() and mark_end() (the timed region) are reported.
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -127,6 +130,13 @@ class ClockSampler:
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
         self.gpu_index = gpu_index
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -148,10 +158,18 @@ class ClockSampler:
         self.f.close()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        import datetime
         for line in open(self.path):
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:
                 continue
+            if self.t0 is not None and self.t1 is not None:
+                try:
+                    ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if ts < self.t0 - 0.05 or ts > self.t1 + 0.05:
+                        continue
+                except ValueError:
+                    pass
             try:
                 sm.append(float(parts[1]))
                 mx.append(float(parts[2]))
@@ -418,21 +436,23 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
     _lib.profile_reset()
     _lib.profile_enable(True)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    sampler.mark_end()
     elapsed_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     prof = _lib.profile_read()

@@ -1,15 +1,16 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/g_tests.log 2>&1
-echo "rc $?" >> gpurun_out/g_tests.log
-tail -5 gpurun_out/g_tests.log
-timeout 1200 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r2_c.json 2> gpurun_out/bench_r2_c.err
-echo "bench rc $?"; tail -3 gpurun_out/bench_r2_c.err | cut -c1-300
+rm -f gpurun_out/ab.log gpurun_out/dump_*.txt
+TF_PROFILE_DUMP=gpurun_out/dump_half.txt python bench.py --frames 96 --steps 2 --warmup 2 --no-e2e --no-cpu-baseline --no-detection 2>&1 | python profiles/tools/ab_parse.py | head -2
+TF_PYR_NO_HALF=1 TF_PROFILE_DUMP=gpurun_out/dump_nohalf.txt python bench.py --frames 96 --steps 2 --warmup 2 --no-e2e --no-cpu-baseline --no-detection 2>&1 | python profiles/tools/ab_parse.py | head -2
 python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_r2_c.json').read().strip().splitlines()[-1])
-print('value',d['value'],'ms',d['ms_per_step'],'frac',d['roofline']['frac'],'whole',d['roofline']['whole_step']['frac'])
-print('e2e',{k:v for k,v in d['e2e'].items() if k!='note'})
-for k,v in d['roofline']['per_class'].items(): print("  %-16s %8.2f ms %6.0f GB/s"%(k,v['ms_per_step'],v['GBps']))
-print(d['clocks'], d.get('detection'))
+for name in ("half","nohalf"):
+    recs=[tuple(map(float,l.split())) for l in open(f"gpurun_out/dump_{name}.txt")]
+    print(name, len(recs))
+    prev_end=None
+    gaps=[]
+    for i,(k,t0,ms) in enumerate(recs):
+        if prev_end is not None and t0-prev_end>0.3: gaps.append((i,int(k),round(t0,2),round(t0-prev_end,2), int(recs[i-1][0])))
+        prev_end=t0+ms
+    print(" gaps>0.3ms:", gaps[:30])
 PY

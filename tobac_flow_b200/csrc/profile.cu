@@ -1,5 +1,7 @@
 // Launch accounting for bench.py: per kernel class, the number of launches, the algorithmic bytes they moved and
 // (when enabled) their device time measured with CUDA events recorded on the launching stream.
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -26,13 +28,22 @@ cudaEvent_t get_event() {
 }
 
 void drain_locked() {
+    // TF_PROFILE_DUMP=file: one line per timed launch group (class, start relative to the first group, duration, ms)
+    static const char* dump_path = getenv("TF_PROFILE_DUMP");
+    FILE* dump = (dump_path && !g_recs.empty()) ? fopen(dump_path, "a") : nullptr;
     for (Rec& r : g_recs) {
         float ms = 0.f;
         if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess)
             g_ms[r.klass] += ms;
+        if (dump) {
+            float t0 = 0.f;
+            cudaEventElapsedTime(&t0, g_recs.front().a, r.a);
+            fprintf(dump, "%d %.4f %.4f\n", r.klass, t0, ms);
+        }
         g_pool.push_back(r.a);
         g_pool.push_back(r.b);
     }
+    if (dump) fclose(dump);
     g_recs.clear();
 }
 }  // namespace

@@ -503,6 +503,74 @@ __global__ void __launch_bounds__(NT) pyr_row_kernel(const uint8_t* __restrict__
     }
 }
 
+// The first down-sampled level when the image halves exactly (W == 2 w, H == 2 h, 3-tap blur): every destination pixel
+// is the same 4 x 4 separable filter (combined taps c = g + dg / 2) of the source pixels (2j - 1 .. 2j + 2) x (2i - 1 ..
+// 2i + 2).  A thread owns eight source columns = four destination columns and walks down the source rows: per row one
+// 64-bit load (the two edge bytes come from the neighbouring lanes), the four horizontal sums, and two vertical updates
+// (a source row feeds the destination row it opens and the one it closes).  ~5 instructions per source pixel instead of the
+// ~40 the general row kernel spends at this level (its per-pixel coordinate and loop overheads dominate a 4-tap filter).
+constexpr int HALF_RJ = 16;      // destination rows per thread
+__global__ void __launch_bounds__(128) pyr_half_kernel(const uint8_t* __restrict__ q0, const uint8_t* __restrict__ q1,
+                                                       float* __restrict__ out, int H, int W, int h, int w, float c0, float c1,
+                                                       float c2, float c3) {
+    const int W8 = (W + 7) >> 3;
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    const bool active = t < W8;
+    const int tc = min(t, W8 - 1);
+    const int xb = 8 * tc;
+    const int img = blockIdx.z;
+    const uint8_t* src = ((img & 1) ? q1 : q0) + (long long)(img >> 1) * H * W;
+    const int j0 = blockIdx.y * HALF_RJ;
+    const int nj = min(HALF_RJ, h - j0);
+    const bool has_hi = xb + 4 < W;                              // W % 4 == 0: the last thread may own one word only
+    const int lane = threadIdx.x & 31;
+    const bool left_edge = lane == 0 || tc == 0, right_edge = lane == 31 || tc == W8 - 1;
+    const int xl = reflect101(xb - 1, W), xr = reflect101(xb + 8, W), xm = reflect101(xb + 4, W);
+    float prev[4] = {0.f, 0.f, 0.f, 0.f}, cur[4] = {0.f, 0.f, 0.f, 0.f};
+    float* orow = out + ((long long)img * h + j0) * w + 4 * tc;
+    const int n_out = max(0, min(4, w - 4 * tc));
+    const bool vec2 = (w & 1) == 0 && n_out == 4;
+    // source rows 2 j0 - 1 .. 2 (j0 + nj): row s (0-based) opens destination row s / 2 with tap s % 2 and feeds row
+    // s / 2 - 1 with tap s % 2 + 2
+    for (int s = 0; s < 2 * nj + 2; ++s) {
+        const uint8_t* row = src + (long long)reflect101(2 * j0 - 1 + s, H) * W;
+        const unsigned lo = __ldg(reinterpret_cast<const unsigned*>(row + xb));
+        const unsigned hi = has_hi ? __ldg(reinterpret_cast<const unsigned*>(row + xb + 4)) : (unsigned)__ldg(row + xm);
+        const unsigned nl = __shfl_up_sync(0xffffffffu, hi, 1), nr = __shfl_down_sync(0xffffffffu, lo, 1);
+        float p[10];
+        p[0] = left_edge ? u8f(__ldg(row + xl)) : byte_to_float(nl, 0x7543u);
+        p[1] = byte_to_float(lo, 0x7540u); p[2] = byte_to_float(lo, 0x7541u);
+        p[3] = byte_to_float(lo, 0x7542u); p[4] = byte_to_float(lo, 0x7543u);
+        p[5] = byte_to_float(hi, 0x7540u); p[6] = byte_to_float(hi, 0x7541u);
+        p[7] = byte_to_float(hi, 0x7542u); p[8] = byte_to_float(hi, 0x7543u);
+        p[9] = right_edge ? u8f(__ldg(row + xr)) : byte_to_float(nr, 0x7540u);
+        const bool odd = s & 1;
+        const float wa = odd ? c1 : c0, wb = odd ? c3 : c2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float hsum = fmaf(c3, p[2 * k + 3], fmaf(c2, p[2 * k + 2], fmaf(c1, p[2 * k + 1], c0 * p[2 * k])));
+            cur[k] = fmaf(wa, hsum, cur[k]);
+            prev[k] = fmaf(wb, hsum, prev[k]);
+        }
+        if (odd) {
+            const int jl = (s >> 1) - 1;                         // the destination row this source row closes
+            if (jl >= 0 && active) {
+                float* o = orow + (long long)jl * w;
+                if (vec2) {
+                    *reinterpret_cast<float2*>(o) = make_float2(prev[0], prev[1]);
+                    *reinterpret_cast<float2*>(o + 2) = make_float2(prev[2], prev[3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < n_out) o[k] = prev[k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { prev[k] = cur[k]; cur[k] = 0.f; }
+        }
+    }
+}
+
 // pass B at the full-resolution level (w == W, no resize), 4 outputs per thread (W % 4 == 0)
 __global__ void __launch_bounds__(256) blur_h4_fullres_kernel(const float* __restrict__ tmp, float* __restrict__ out, int W,
                                                               int h, BlurTaps taps) {
@@ -685,6 +753,19 @@ int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int 
             rt.dg[c] = gm - gc;
         }
         for (int c = ksize + 1; c <= kMaxBlurTaps; ++c) rt.g[c] = rt.dg[c] = 0.f;
+        static const char* env_half = getenv("TF_PYR_NO_HALF");   // A/B: the general row kernel at the half-resolution level
+        if (ksize == 3 && W == 2 * w && H == 2 * h && env_half == nullptr) {
+            const float c0 = rt.g[0] + 0.5f * rt.dg[0], c1 = rt.g[1] + 0.5f * rt.dg[1], c2 = rt.g[2] + 0.5f * rt.dg[2],
+                        c3 = rt.g[3] + 0.5f * rt.dg[3];
+            LaunchTimer lt(KC_PYRAMID, (2.0 * H * W + 8.0 * h * w) * n_pairs, s, cdiv(n_img, 65534));
+            for (int z0 = 0; z0 < n_img; z0 += 65534) {
+                const int nz = min(n_img - z0, 65534);
+                dim3 g(cdiv((W + 7) / 8, 128), cdiv(h, HALF_RJ), nz);
+                pyr_half_kernel<<<g, 128, 0, s>>>(q0 + (long long)(z0 / 2) * H * W, q1 + (long long)(z0 / 2) * H * W,
+                                                  out + (long long)z0 * h * w, H, W, h, w, c0, c1, c2, c3);
+            }
+            return check_launch("pyramid level (half)");
+        }
         const int W4 = W >> 2;
         const size_t smem = (size_t)(W + W / 32 + 8) * sizeof(float);
         // threads: the W / 4 column words in an even number of rounds of two words per thread
