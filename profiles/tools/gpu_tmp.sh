@@ -1,16 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-rm -f gpurun_out/ab.log gpurun_out/dump_*.txt
-TF_PROFILE_DUMP=gpurun_out/dump_half.txt python bench.py --frames 96 --steps 2 --warmup 2 --no-e2e --no-cpu-baseline --no-detection 2>&1 | python profiles/tools/ab_parse.py | head -2
-TF_PYR_NO_HALF=1 TF_PROFILE_DUMP=gpurun_out/dump_nohalf.txt python bench.py --frames 96 --steps 2 --warmup 2 --no-e2e --no-cpu-baseline --no-detection 2>&1 | python profiles/tools/ab_parse.py | head -2
-python - <<'PY'
-for name in ("half","nohalf"):
-    recs=[tuple(map(float,l.split())) for l in open(f"gpurun_out/dump_{name}.txt")]
-    print(name, len(recs))
-    prev_end=None
-    gaps=[]
-    for i,(k,t0,ms) in enumerate(recs):
-        if prev_end is not None and t0-prev_end>0.3: gaps.append((i,int(k),round(t0,2),round(t0-prev_end,2), int(recs[i-1][0])))
-        prev_end=t0+ms
-    print(" gaps>0.3ms:", gaps[:30])
-PY
+B="python bench.py --frames 8 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-detection"
+$B > /dev/null 2>&1 || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"fb_iter|sl_gather|sl_lean|sobel_lin|pyr_|blur|polyexp|flow_upsample|pair_|minmax|finalise" -c 400 --csv --log-file gpurun_out/launches_r2_final.csv $B > gpurun_out/ncu_launches_final.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"sobel_lin|sl_lean|pyr_half|pyr_row" -c 9 -o gpurun_out/r2_prof_small_final -f $B > gpurun_out/ncu_small_final.log 2>&1
+tail -2 gpurun_out/ncu_small_final.log | cut -c1-200
