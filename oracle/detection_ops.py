@@ -19,6 +19,9 @@ Reference lines followed:
   filtered_tdiff            tobac_flow/detection.py:34-60
   get_curvature_filter      tobac_flow/detection.py:64-94
   detect_growth_markers     tobac_flow/detection.py:98-125
+  nan_gaussian_filter       tobac_flow/detection.py:128-146
+  detect_growth_markers_multichannel   tobac_flow/detection.py:203-254
+                            (filter_labels_by_length_and_multimask_legacy analysis.py:182-201)
   get_growth_rate           tobac_flow/detection.py:168-198
   get_anvil_markers         tobac_flow/detection.py:494-516 (find_object_lengths analysis.py:15-35,
                             remap_labels utils/label_utils.py:265-307)
@@ -172,6 +175,63 @@ def detect_growth_markers(wvd, dt_minutes, fwd, bwd, backend="numpy", intermedia
     if intermediates:
         return dict(raw=raw, smoothed=smoothed, filtered=filtered, seeds=seeds, linked=linked, markers=markers)
     return smoothed, markers
+
+
+def nan_gaussian_filter(a, *args, propagate_nan=True, **kwargs):
+    """detection.py:128-146."""
+    wh_nan = np.isnan(a)
+    a0 = a.copy()
+    a0[wh_nan] = 0
+    c = np.ones_like(a)
+    c[wh_nan] = 0
+    a0_gaussian = ndi.gaussian_filter(a0, *args, **kwargs)
+    c_gaussian = ndi.gaussian_filter(c, *args, **kwargs)
+    c_gaussian[c_gaussian == 0] = np.nan
+    with np.errstate(invalid="ignore", divide="ignore"):
+        result = a0_gaussian / c_gaussian
+    if propagate_nan:
+        result[wh_nan] = np.nan
+    return result
+
+
+def filter_labels_by_length_and_multimask_legacy(labels, masks, min_length):
+    """analysis.py:182-201 (labels is renumbered in place by the reference; a copy here)."""
+    if type(masks) is not type(list()):
+        raise ValueError("masks input must be a list of masks to process")
+    labels = labels.copy()
+    bins = np.cumsum(np.bincount(labels.ravel()))
+    args = np.argsort(labels.ravel())
+    object_lengths = np.array([o[0].stop - o[0].start for o in ndi.find_objects(labels)])
+    counter = 1
+    for i in range(bins.size - 1):
+        if bins[i + 1] > bins[i]:
+            sel = args[bins[i]:bins[i + 1]]
+            if object_lengths[i] >= min_length and np.all([np.any(m.ravel()[sel]) for m in masks]):
+                labels.ravel()[sel] = counter
+                counter += 1
+            else:
+                labels.ravel()[sel] = 0
+    return labels
+
+
+def detect_growth_markers_multichannel(wvd, bt, dt_wvd, dt_bt, fwd, bwd, overlap=0.5, min_length=4, lower_threshold=0.25,
+                                       upper_threshold=0.5, backend="numpy"):
+    """detection.py:203-254 on plain (T, H, W) arrays (subsegment_shrink = 0)."""
+    wvd, bt = np.asarray(wvd), np.asarray(bt)
+    wvd_s = filtered_tdiff(ops.diff(wvd, fwd, bwd, backend=backend)
+                           / np.asarray(dt_wvd, np.float64)[:, np.newaxis, np.newaxis], fwd, bwd, backend=backend)
+    bt_s = filtered_tdiff(ops.diff(bt, fwd, bwd, backend=backend)
+                          / np.asarray(dt_bt, np.float64)[:, np.newaxis, np.newaxis], fwd, bwd, backend=backend)
+    with np.errstate(invalid="ignore"):
+        markers = np.logical_or((wvd_s * get_curvature_filter(wvd)) >= lower_threshold,
+                                (bt_s * get_curvature_filter(bt, direction="positive")) <= -lower_threshold)
+    seeds = ndi.binary_opening(markers, structure=ndi.generate_binary_structure(2, 1)[np.newaxis, ...])
+    markers = flow_label(seeds, fwd, bwd, overlap=overlap, absolute_overlap=1, backend=backend)
+    if np.count_nonzero(markers) > 0:
+        with np.errstate(invalid="ignore"):
+            markers = filter_labels_by_length_and_multimask_legacy(
+                markers, [wvd_s >= upper_threshold, bt_s <= -upper_threshold, wvd > -5], min_length)
+    return wvd_s, bt_s, markers
 
 
 def get_growth_rate(field, dt_minutes, fwd, bwd, method="linear", backend="numpy"):

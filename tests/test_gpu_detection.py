@@ -243,6 +243,55 @@ def test_detect_growth_markers_with_own_flow_and_nans():
     assert want["markers"].max() >= 1
 
 
+def test_detect_growth_markers_multichannel_and_nan_gaussian(multi):
+    """detection.py:203-254 and :128-146 on the device against the oracle (itself checked against the unmodified
+    reference in tests/test_oracle_detection.py): both smoothed rates and the marker labels bit-exact, with NaN pixels in
+    both channels and non-default thresholds; the legacy multi-mask label filter on its own."""
+    import pandas as pd
+    import refshim
+    from tobac_flow_b200 import analysis
+    from tobac_flow_b200.detection import detect_growth_markers_multichannel, nan_gaussian_filter
+    g, wvd, fwd, bwd, flow = multi
+    wvd = wvd.copy()
+    bt = (250.0 - 2.2 * (wvd + 25.0)).astype(np.float32)
+    wvd[6, 40:42, 50:80] = np.nan
+    bt[3, 70, 10:40] = np.nan
+    t = pd.date_range("2020-01-01", periods=wvd.shape[0], freq="5min")
+    da_w = refshim.DataArray(wvd, coords={"t": t}, dims=("t", "y", "x"), t=t)
+    da_b = refshim.DataArray(bt, coords={"t": t}, dims=("t", "y", "x"), t=t)
+    dt = np.full(wvd.shape[0], 5.0)
+    for kw in (dict(), dict(overlap=0.2, min_length=2, lower_threshold=0.2, upper_threshold=0.4)):
+        got = detect_growth_markers_multichannel(flow, da_w, da_b, **kw)
+        want = det.detect_growth_markers_multichannel(wvd, bt, dt, dt, fwd, bwd, backend=BACKEND, **kw)
+        for a, b in zip(got, want):
+            a = np.asarray(a.data if hasattr(a, "data") and not isinstance(a, np.ndarray) else a)
+            assert a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True)
+        assert want[2].max() >= 1
+    with pytest.raises(NotImplementedError):
+        detect_growth_markers_multichannel(flow, da_w, da_b, subsegment_shrink=0.5)
+    # the label filter alone: three masks, odd count
+    lab = g["linked"].astype(np.int32)
+    rng = np.random.default_rng(3)
+    masks = [rng.random(lab.shape) > 0.9995, rng.random(lab.shape) > 0.999, wvd > -12]
+    assert np.array_equal(analysis.filter_labels_by_length_and_multimask_legacy(lab, masks, 3),
+                          det.filter_labels_by_length_and_multimask_legacy(lab, masks, 3))
+    with pytest.raises(ValueError):
+        analysis.filter_labels_by_length_and_multimask_legacy(lab, tuple(masks), 3)
+    # nan_gaussian_filter
+    x = wvd[:4].copy()
+    x[2] = np.nan
+    x[1, :, 50] = np.nan
+    for dtype in (np.float32, np.float64):
+        for prop in (True, False):
+            got = nan_gaussian_filter(x.astype(dtype), (0, 2, 2), propagate_nan=prop)
+            want = det.nan_gaussian_filter(x.astype(dtype), (0, 2, 2), propagate_nan=prop)
+            assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=True)
+    got = nan_gaussian_filter(x[0], 1.5)
+    assert np.array_equal(got, det.nan_gaussian_filter(x[0], 1.5), equal_nan=True)
+    with pytest.raises(NotImplementedError):
+        nan_gaussian_filter(x, (0, 2, 2), mode="nearest")
+
+
 @pytest.mark.parametrize("method", ["linear", "cubic"])
 def test_get_growth_rate(multi, method):
     import pandas as pd

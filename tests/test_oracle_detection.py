@@ -164,3 +164,51 @@ def test_growth_rate_and_anvil_markers_against_the_unmodified_reference(multi):
             if name.split(".")[0] in ("tobac_flow", "xarray", "pyproj", "skimage"):
                 del sys.modules[name]
         refshim._loaded = None
+
+
+def _bt_companion(wvd):
+    """A window brightness temperature that cools where the water-vapour difference grows (monotone map + offset)."""
+    return (250.0 - 2.2 * (wvd + 25.0)).astype(np.float32)
+
+
+def test_multichannel_markers_and_nan_gaussian_against_the_unmodified_reference(multi):
+    """Build container only: the oracle's detect_growth_markers_multichannel, its legacy multi-mask label filter and
+    nan_gaussian_filter against the reference's own functions run under the dependency stubs."""
+    import refshim
+    if not refshim.reference_available():
+        pytest.skip("reference not available")
+    import sys
+    import pandas as pd
+    saved_path, saved_modules = list(sys.path), set(sys.modules)
+    try:
+        refshim.load_reference()
+        from tobac_flow.flow import Flow
+        from tobac_flow import detection
+        g, wvd, fwd, bwd, r = multi
+        bt = _bt_companion(wvd)
+        fl = Flow(fwd, bwd)
+        t = pd.date_range("2020-01-01", periods=wvd.shape[0], freq="5min")
+        da_w = refshim.DataArray(wvd, coords={"t": t}, dims=("t", "y", "x"), t=t)
+        da_b = refshim.DataArray(bt, coords={"t": t}, dims=("t", "y", "x"), t=t)
+        dt = np.full(wvd.shape[0], 5.0)
+        for kw in (dict(), dict(overlap=0.2, min_length=2, lower_threshold=0.2, upper_threshold=0.4)):
+            want = detection.detect_growth_markers_multichannel(fl, da_w, da_b, **kw)
+            got = det.detect_growth_markers_multichannel(wvd, bt, dt, dt, fwd, bwd, backend="cv2", **kw)
+            for a, b in zip(want, got):
+                a = np.asarray(a.data if hasattr(a, "data") and not isinstance(a, np.ndarray) else a)
+                assert np.array_equal(a, b, equal_nan=True)
+            assert got[2].max() >= 1
+        x = wvd[:3].copy()
+        x[0, 10:14, 20:30] = np.nan
+        x[1, :, 50] = np.nan
+        x[2] = np.nan
+        for args in (((0, 2, 2),), ((0, 1.5, 1.5),)):
+            assert np.array_equal(detection.nan_gaussian_filter(x, *args), det.nan_gaussian_filter(x, *args), equal_nan=True)
+            assert np.array_equal(detection.nan_gaussian_filter(x, *args, propagate_nan=False),
+                                  det.nan_gaussian_filter(x, *args, propagate_nan=False), equal_nan=True)
+    finally:
+        sys.path[:] = saved_path
+        for name in set(sys.modules) - saved_modules:
+            if name.split(".")[0] in ("tobac_flow", "xarray", "pyproj", "skimage"):
+                del sys.modules[name]
+        refshim._loaded = None

@@ -94,3 +94,25 @@ def filter_labels_by_length_and_mask(labels, mask, min_length):
     n_labels, tmin, tmax, any_a, _ = label_stats_device(lab, m)
     wh = np.logical_and((tmax[1:] - tmin[1:] + 1) >= min_length, any_a[1:] != 0)
     return _finish(_apply_keep(lab, n_labels, wh), host, np_dtype)
+
+
+def filter_labels_by_length_and_multimask_legacy(labels, masks, min_length):
+    """analysis.py:182-201: keep labels whose extent along axis 0 is >= min_length and that touch EVERY mask of the list;
+    renumber in ascending label order."""
+    if type(masks) is not type(list()):
+        raise ValueError("masks input must be a list of masks to process")
+    lab, host, np_dtype = _labels_device(labels)
+    wh = None
+    n_labels = 0
+    ms = [_mask_device(m, lab.shape) for m in masks]
+    for k in range(0, max(len(ms), 1), 2):
+        ma = ms[k] if k < len(ms) else None
+        mb = ms[k + 1] if k + 1 < len(ms) else None
+        n_labels, tmin, tmax, any_a, any_b = label_stats_device(lab, ma, mb)
+        ok = (tmax[1:] - tmin[1:] + 1) >= min_length
+        if ma is not None:
+            ok = np.logical_and(ok, any_a[1:] != 0)
+        if mb is not None:
+            ok = np.logical_and(ok, any_b[1:] != 0)
+        wh = ok if wh is None else np.logical_and(wh, ok)
+    return _finish(_apply_keep(lab, n_labels, wh), host, np_dtype)

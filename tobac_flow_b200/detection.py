@@ -248,6 +248,118 @@ def detect_growth_markers(flow, wvd):
     return smoothed, markers
 
 
+def nan_gaussian_filter(a, *args, propagate_nan=True, **kwargs):
+    """detection.py:128-146: Gaussian filter that ignores NaNs (filtered values / filtered weights).  Built for the
+    per-frame filter the reference's callers use -- a (t, y, x) field with sigma = (0, s, s), or one (y, x) frame with a
+    scalar sigma -- in scipy's default mode; other ``gaussian_filter`` arguments are not built."""
+    if kwargs or len(args) != 1:
+        raise NotImplementedError("nan_gaussian_filter: only the sigma argument of gaussian_filter is supported")
+    sigma = args[0]
+    t, host = _to_device(a)
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)
+    squeeze = t.dim() == 2
+    if squeeze:
+        t = t[None]
+        s_yx = (sigma, sigma) if np.isscalar(sigma) else tuple(sigma)
+    else:
+        if np.isscalar(sigma) or len(sigma) != 3 or sigma[0] != 0:
+            raise NotImplementedError("nan_gaussian_filter: a (t, y, x) field needs sigma = (0, s, s)")
+        s_yx = (sigma[1], sigma[2])
+    if t.dim() != 3 or s_yx[0] != s_yx[1]:
+        raise NotImplementedError("nan_gaussian_filter: equal y / x sigmas on (y, x) or (t, y, x) fields only")
+    t = t.contiguous()
+    wh_nan = torch.isnan(t)
+    a0 = torch.where(wh_nan, torch.zeros_like(t), t)
+    c = torch.where(wh_nan, torch.zeros_like(t), torch.ones_like(t))
+    a0_g = gaussian_filter_yx_device(a0, float(s_yx[0]))
+    c_g = gaussian_filter_yx_device(c, float(s_yx[0]))
+    c_g = torch.where(c_g == 0, torch.full_like(c_g, float("nan")), c_g)
+    result = a0_g / c_g
+    if propagate_nan:
+        result = torch.where(wh_nan, torch.full_like(result, float("nan")), result)
+    if squeeze:
+        result = result[0]
+    return _to_host(result) if host else result
+
+
+def growth_markers_multichannel_device(flow: Flow, wvd: torch.Tensor, bt: torch.Tensor, dt_wvd, dt_bt, overlap=0.5,
+                                       min_length=4, lower_threshold=0.25, upper_threshold=0.5) -> dict:
+    """detection.py:203-254 on device tensors (``subsegment_shrink == 0``): growth of the water-vapour difference OR
+    cooling of the window brightness temperature, each inside its curvature filter."""
+    lib = _lib.load()
+    dev = wvd.device
+    T, H, W = wvd.shape
+    n = wvd.numel()
+    st = _stream
+
+    def smoothed_rate(field, dt_minutes):
+        raw32 = flow.diff(field)
+        dt = torch.from_numpy(np.ascontiguousarray(np.asarray(dt_minutes, np.float64))).to(dev)
+        assert dt.numel() == T
+        raw = torch.empty((T, H, W), dtype=torch.float64, device=dev)
+        _lib.check(lib.tf_scale_frames(raw32.data_ptr(), dt.data_ptr(), raw.data_ptr(), T, H, W, st()), "tf_scale_frames")
+        return filtered_tdiff(flow, raw)
+
+    def times_mask(x, mask):
+        out = torch.empty_like(x)
+        _lib.check(lib.tf_mask_multiply(x.data_ptr(), mask.data_ptr(), out.data_ptr(), _float_code(x), n, st()),
+                   "tf_mask_multiply")
+        return out
+
+    def ge(x, thr):
+        m = torch.empty((T, H, W), dtype=torch.uint8, device=dev)
+        _lib.check(lib.tf_threshold_ge(x.data_ptr(), float(thr), m.data_ptr(), _float_code(x), n, st()), "tf_threshold_ge")
+        return m
+
+    wvd_s = smoothed_rate(wvd, dt_wvd)                                                  # :214-217
+    bt_s = smoothed_rate(bt, dt_bt)                                                     # :218-220
+    grow = ge(times_mask(wvd_s, curvature_filter_device(wvd)), lower_threshold)         # :223
+    cool = ge(-times_mask(bt_s, curvature_filter_device(bt, direction="positive")), lower_threshold)   # :224-225 (x <= -l)
+    seeds_in = torch.bitwise_or(grow, cool)
+    seeds = torch.empty_like(seeds_in)
+    _lib.check(lib.tf_binary_opening_cross(seeds_in.data_ptr(), seeds.data_ptr(), T, H, W, st()), "tf_binary_opening_cross")
+    flat, n_flat = _label.flat_label_device(seeds, 1)                                   # Flow.label(overlap=overlap), :227-233
+    linked, _ = _label.link_overlap_device(flow, flat, _label._default_structure(), overlap, 1, n_flat)
+    markers = linked
+    if bool((linked != 0).any()):                                                       # :236-246
+        masks = [ge(wvd_s, upper_threshold), ge(-bt_s, upper_threshold), (wvd > -5).to(torch.uint8)]
+        markers = analysis.filter_labels_by_length_and_multimask_legacy(linked, masks, min_length)
+    else:
+        import warnings
+        warnings.warn("No regions detected in labeled array", RuntimeWarning)
+    return dict(wvd_diff_smoothed=wvd_s, bt_diff_smoothed=bt_s, seeds=seeds, linked=linked, markers=markers)
+
+
+def detect_growth_markers_multichannel(flow, wvd, bt, t_sigma=1, overlap=0.5, subsegment_shrink=0, min_length=4,
+                                       lower_threshold=0.25, upper_threshold=0.5):
+    """detection.py:203-254: returns (wvd_diff_smoothed, bt_diff_smoothed, markers).  ``wvd`` and ``bt`` carry a ``.t``
+    time coordinate; CUDA tensors (with a ``t`` attribute) keep the results on the device."""
+    if subsegment_shrink != 0:
+        raise NotImplementedError("subsegment_shrink != 0 (skimage watershed sub-segmentation) is not built here")
+    if getattr(wvd, "t", None) is None or getattr(bt, "t", None) is None:
+        raise AttributeError("wvd and bt need a time coordinate `.t` (detection.py:216, 219)")
+    on_device = isinstance(wvd, torch.Tensor) and wvd.is_cuda
+    w, _ = _to_device(wvd if isinstance(wvd, torch.Tensor) else _as_numpy(wvd))
+    b, _ = _to_device(bt if isinstance(bt, torch.Tensor) else _as_numpy(bt))
+    if w.dtype not in (torch.float32, torch.float64):
+        w = w.to(torch.float32)
+    if b.dtype not in (torch.float32, torch.float64):
+        b = b.to(torch.float32)
+    r = growth_markers_multichannel_device(flow, w.contiguous(), b.contiguous(), time_diff_minutes(wvd.t),
+                                           time_diff_minutes(bt.t), overlap, min_length, lower_threshold, upper_threshold)
+    if on_device:
+        return r["wvd_diff_smoothed"], r["bt_diff_smoothed"], r["markers"]
+    out = [_to_host(r["wvd_diff_smoothed"]), _to_host(r["bt_diff_smoothed"]), _to_host(r["markers"])]
+    if hasattr(wvd, "coords") and hasattr(wvd, "dims") and not isinstance(wvd, np.ndarray):
+        try:
+            out = [type(wvd)(out[0], wvd.coords, wvd.dims), type(bt)(out[1], bt.coords, bt.dims),
+                   type(wvd)(out[2], wvd.coords, wvd.dims)]                             # detection.py:249-252
+        except Exception:
+            pass
+    return tuple(out)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # watershed inputs (detection.py:575-642): the edge field the anvil watershed floods, and its mask
 # ------------------------------------------------------------------------------------------------------------------
