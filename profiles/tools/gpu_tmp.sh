@@ -1,5 +1,6 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_detection.py -x -q -m gpu > gpurun_out/j_tests.log 2>&1
-echo "rc $?" >> gpurun_out/j_tests.log
-tail -25 gpurun_out/j_tests.log
+for v in "" b4m8 b4m9 b4m10 b2m18 ""; do
+  echo "== variant $v"
+  if [ -n "$v" ]; then export TF_LIB_PATH=$PWD/profiles/tools/_var/libtf_$v.so; else unset TF_LIB_PATH; fi
+  python profiles/tools/gather_time.py 2>&1 | grep "sobel"
+done

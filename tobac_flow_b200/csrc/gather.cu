@@ -645,14 +645,19 @@ __device__ __forceinline__ bool sobel_patch_nans(float v[9], float centre, int s
 }
 
 #ifndef TF_SOBEL_MINB
-#define TF_SOBEL_MINB 4
+#define TF_SOBEL_MINB 8
 #endif
 // rows per thread: 1 (measured, ms per 24 CONUS frames: 2.07 with one row, 2.32-2.35 with 2 or 4 rows and the next row's
 // flow vectors requested ahead -- the loop-carried state spills at 64 registers, and 80 registers cost a CTA per SM)
 #ifndef TF_SOBEL_ROWS
 #define TF_SOBEL_ROWS 1
 #endif
-__global__ void __launch_bounds__(256, TF_SOBEL_MINB) sobel_lin_f64_kernel(GatherArgs a) {
+// block = 32 x TF_SOBEL_BY pixels (measured, ms per 24 CONUS frames: 32 x 4 at 8 CTAs per SM 2.00, 32 x 8 at 4 CTAs 2.07,
+// 32 x 4 at 9 / 10 CTAs (56 / 48 registers, spills) 2.02 / 2.06)
+#ifndef TF_SOBEL_BY
+#define TF_SOBEL_BY 4
+#endif
+__global__ void __launch_bounds__(32 * TF_SOBEL_BY, TF_SOBEL_MINB) sobel_lin_f64_kernel(GatherArgs a) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int t = blockIdx.z;
     const int H = a.H, W = a.W;
@@ -665,13 +670,13 @@ __global__ void __launch_bounds__(256, TF_SOBEL_MINB) sobel_lin_f64_kernel(Gathe
     const unsigned lim_x = patch_limit(W), lim_y = patch_limit(H);
     // a thread walks TF_SOBEL_ROWS rows, 8 apart, and requests the flow vectors of its next row before it works on the
     // current one (they are the head of the pixel's dependent load chain)
-    int y = blockIdx.y * (8 * TF_SOBEL_ROWS) + threadIdx.y;
+    int y = blockIdx.y * (TF_SOBEL_BY * TF_SOBEL_ROWS) + threadIdx.y;
     float2 bf_n = make_float2(0.f, 0.f), ff_n = bf_n;
     if (y < H && inner_xt) { bf_n = __ldg(bfl + y * W + x); ff_n = __ldg(ffl + y * W + x); }
 #pragma unroll 1
-    for (int k = 0; k < TF_SOBEL_ROWS && y < H; ++k, y += 8) {
+    for (int k = 0; k < TF_SOBEL_ROWS && y < H; ++k, y += TF_SOBEL_BY) {
     const float2 bf = bf_n, ff = ff_n;
-    if (k + 1 < TF_SOBEL_ROWS && y + 8 < H && inner_xt) { bf_n = __ldg(bfl + (y + 8) * W + x); ff_n = __ldg(ffl + (y + 8) * W + x); }
+    if (k + 1 < TF_SOBEL_ROWS && y + TF_SOBEL_BY < H && inner_xt) { bf_n = __ldg(bfl + (y + TF_SOBEL_BY) * W + x); ff_n = __ldg(ffl + (y + TF_SOBEL_BY) * W + x); }
     const int pix = y * W + x;
     double* out = reinterpret_cast<double*>(a.out) + (long long)t * hw + pix;
     const bool inner = inner_xt && y >= 1 && y < H - 1;
@@ -773,7 +778,7 @@ static int launch_sobel_fast(const GatherArgs& a, cudaStream_t s) {
         b.n_frames = nt;
         b.has_prev = (t0 > 0) ? 1 : a.has_prev;
         b.has_next = (t0 + nt < a.n_frames) ? 1 : a.has_next;
-        sobel_lin_f64_kernel<<<dim3(cdiv(a.W, 32), cdiv(a.H, 8 * TF_SOBEL_ROWS), nt), dim3(32, 8), 0, s>>>(b);
+        sobel_lin_f64_kernel<<<dim3(cdiv(a.W, 32), cdiv(a.H, TF_SOBEL_BY * TF_SOBEL_ROWS), nt), dim3(32, TF_SOBEL_BY), 0, s>>>(b);
     }
     return check_launch("tf_sl_convolve (sobel)");
 }
