@@ -22,6 +22,7 @@ is 288*N frames, time-sharded one day per rank with NCCL point-to-point halo exc
 frames of work), and prints the same JSON line with "impl": "reference".
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -445,6 +446,10 @@ def run_b200(args):
     _lib.profile_reset()
     _lib.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # The timed region starts with an empty launch queue, so a host pause before the first launches is fully exposed
+    # (6-50 ms gaps showed up in some runs): no cyclic garbage collection inside the region.
+    gc.collect()
+    gc.disable()
     barrier()
     sampler.mark_begin()
     e0.record()
@@ -453,6 +458,7 @@ def run_b200(args):
     e1.record()
     barrier()
     sampler.mark_end()
+    gc.enable()
     elapsed_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     prof = _lib.profile_read()
