@@ -1,18 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python __graft_entry__.py smoke > gpurun_out/l_smoke.log 2>&1; echo "smoke rc $?"; tail -2 gpurun_out/l_smoke.log
-timeout 1700 python -m pytest tests -q -m gpu > gpurun_out/l_tests.log 2>&1
-echo "rc $?" >> gpurun_out/l_tests.log
-tail -3 gpurun_out/l_tests.log
-python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r2_final2.json 2> gpurun_out/bench_r2_final2.err
-echo "bench rc $?"; tail -2 gpurun_out/bench_r2_final2.err | cut -c1-200
-python - <<'PY'
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/n_tests.log 2>&1
+echo "rc $?" >> gpurun_out/n_tests.log; tail -2 gpurun_out/n_tests.log
+for i in 1 2; do
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r2_final3_$i.json 2> gpurun_out/bench_r2_final3_$i.err
+python - <<PY
 import json
-d=json.loads(open('gpurun_out/bench_r2_final2.json').read().strip().splitlines()[-1])
+d=json.loads(open('gpurun_out/bench_r2_final3_$i.json').read().strip().splitlines()[-1])
 r=d['roofline']
-print('value',d['value'],'ms',d['ms_per_step'],'whole',r['whole_step']['frac'],'dom',r['frac'],'launches',d['gpu_launches'])
-print('e2e',{k:v for k,v in d['e2e'].items() if k!='note'})
-tot=0
-for k,v in r['per_class'].items(): print('  %-16s %8.2f ms %s'%(k,v['ms_per_step'],v['GBps'])); tot+=v['ms_per_step']
-print('classes',tot, d['clocks'])
+tot=sum(v['ms_per_step'] for v in r['per_class'].values())
+print('run $i value',round(d['value'],1),'ms',round(d['ms_per_step'],1),'classes',round(tot,1),'whole',round(r['whole_step']['frac'],4),'dom',round(r['frac'],4),'e2e',round(d['e2e']['value'],1),round(d['e2e']['value_diff_sobel_convolve_order'],1), d['clocks']['sm_mhz'])
 PY
+done

@@ -707,15 +707,26 @@ def _pair_batch(n_pairs: int, H: int, W: int, params, vr: bool = False) -> int:
     quantisation and the latency-bound launches of the small pyramid levels: 28.4 vs 30.5 ms per 96 CONUS frames for
     the coarse levels at 512 vs 256 Mpx), in equally sized batches (a small last batch would run at a fraction of the
     efficiency)."""
+    # (the answer for a shape is remembered: `cudaMemGetInfo` is a driver call that can wait milliseconds behind a
+    # monitoring query -- nvidia-smi -- and it sits in front of a call's first kernel launch; a shape whose workspace
+    # allocation fails later drops its entry, see calculate_flow_device)
+    key = (torch.cuda.current_device(), n_pairs, H, W, bool(vr), params.num_levels, os.environ.get("TF_PAIR_BATCH_MPX"))
+    if key in _PAIR_BATCH_CACHE:
+        return _PAIR_BATCH_CACHE[key]
     per_pair = _lib.workspace_bytes(1, H, W, params) + 2 * H * W
     if vr:
         per_pair += int(_lib.load().tf_vr_workspace_bytes(1, H, W))
     free, _ = torch.cuda.mem_get_info()
+    free += max(0, torch.cuda.memory_reserved() - torch.cuda.memory_allocated())   # blocks torch holds but can reuse
     by_mem = max(1, int(free * 0.6) // per_pair)
     by_px = max(1, (int(os.environ.get("TF_PAIR_BATCH_MPX", "512")) << 20) // (H * W))
     nb = max(1, min(n_pairs, by_mem, by_px))
     n_batches = -(-n_pairs // nb)
-    return -(-n_pairs // n_batches)
+    _PAIR_BATCH_CACHE[key] = -(-n_pairs // n_batches)
+    return _PAIR_BATCH_CACHE[key]
+
+
+_PAIR_BATCH_CACHE = {}
 
 
 def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Tensor, smoothing_passes: int = 0,
@@ -750,7 +761,11 @@ def calculate_flow_device(frames: torch.Tensor, fwd: torch.Tensor, bwd: torch.Te
     mm = torch.empty((2 * nb,), dtype=frames.dtype, device=dev)
     normalise = lib.tf_pair_normalise_u8_f64 if f64 else lib.tf_pair_normalise_u8
     ws_bytes = _lib.workspace_bytes(nb, H, W, params)
-    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    try:
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    except torch.cuda.OutOfMemoryError:
+        _PAIR_BATCH_CACHE.clear()          # the remembered batch size no longer fits: the next call asks the driver again
+        raise
     vr_params = vr_ws = None
     vr_bytes = 0
     if use_vr:
