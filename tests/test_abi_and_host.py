@@ -155,3 +155,16 @@ def test_detection_host_helpers():
         assert np.array_equal(w, _filters._gaussian_kernel1d(sigma, 0, r))
     t = pd.to_datetime(["2020-01-01 00:00", "2020-01-01 00:05", "2020-01-01 00:15", "2020-01-01 00:16"])
     assert np.array_equal(time_diff_minutes(t), [5.0, 7.5, 5.5, 1.0])
+
+
+def test_host_batch_plan():
+    """Pair batches of the host path: small first (operators can start while the upload runs), doubling up to the device
+    path's batch size; every pair exactly once."""
+    from tobac_flow_b200 import flow as tflow
+    for n_pairs, big in ((287, 96), (287, 143), (44, 44), (7, 96), (1, 1), (100, 5), (16, 8)):
+        plan = tflow._host_batch_plan(n_pairs, big)
+        assert sum(plan) == n_pairs and all(0 < n <= big for n in plan)
+        assert plan[0] == min(tflow._HOST_PAIR_BATCH, n_pairs, big)
+        assert all(b <= 2 * a for a, b in zip(plan, plan[1:-1]))        # at most doubling (the last batch is the remainder)
+    assert tflow._host_batch_plan(287, 96) == [8, 16, 32, 64, 96, 71]
+    assert tflow._host_batch_plan(0, 96) == []
