@@ -95,7 +95,8 @@ long long tf_fb_r_stride(int h, int w);
 int tf_fb_polyexp(const float* I, int n_img, int h, int w, const tf_fb_params* p /* host */, float* R, void* stream);
 
 /* Which fused-iteration kernel tf_farneback_pairs launches: 3 = the default (TMA-staged rows, tensor-memory ring, packed
- * fp32, two rows of gathers in flight), 4 = the same with one row in flight, 0 = the scalar LDG / shared-memory kernel,
+ * fp32, two rows of gathers in flight, the flow up-sampling of a level fused into its first iteration), 4 = the same with
+ * one row in flight, 5 = 3 with the up-sampling in its own kernel, 0 = the scalar LDG / shared-memory kernel,
  * 1 = the scalar kernel with its ring in tensor memory.  For A/B measurements and cross-check tests; the environment
  * variable TF_TMA sets the initial choice. */
 int tf_fb_select_kernel(int which);

@@ -501,15 +501,17 @@ def test_iteration_kernels_agree(tfb):
         for shape in ((3, 100, 100), (3, 97, 131), (2, 150, 258), (2, 64, 1101)):
             bt = synthetic.bt_sequence(shape[0], shape[1], shape[2], seed=77 + shape[2], nans=True)
             res = {}
-            for k in (0, 1, 3, 4):
+            for k in (0, 1, 3, 4, 5):
                 _lib.check(lib.tf_fb_select_kernel(k), "tf_fb_select_kernel")
                 f = tfb.create_flow(bt)
                 res[k] = (f.forward_flow.copy(), f.backward_flow.copy())
             assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])   # ring placement only
             assert np.array_equal(res[3][0], res[4][0]) and np.array_equal(res[3][1], res[4][1])   # lookahead depth only
+            # the flow up-sampling fused into a level's first iteration gives the bits of the separate kernel
+            assert np.array_equal(res[3][0], res[5][0]) and np.array_equal(res[3][1], res[5][1])
             for a, b in zip(res[0], res[3]):
-                assert np.abs(a - b).max() <= 2e-5, np.abs(a - b).max()
-        assert lib.tf_fb_select_kernel(2) < 0
+                assert np.abs(a - b).max() <= 4e-5, np.abs(a - b).max()
+        assert lib.tf_fb_select_kernel(2) < 0 and lib.tf_fb_select_kernel(6) < 0
     finally:
         lib.tf_fb_select_kernel(3)
 

@@ -50,6 +50,7 @@ struct Workspace {
     float* I;      // level images          (2P, h, w)
     float* R;      // polynomial expansion  (2P, 5, h, w)
     float* flow[3];  // (P, 2, h, w, 2) ping / pong / previous level
+    int* tab;        // resize tables of the fused flow up-sampling: x0 (W) | fx (W) | y0 (H) | fy (H)
     size_t total;
 };
 
@@ -69,6 +70,7 @@ static Workspace carve(void* base, int n_pairs, int H, int W, const LevelPlan& l
     };
     const size_t o_tmp = take(2 * P * tmp_px * 4), o_I = take(2 * P * N * 4), o_R = take(2 * P * (size_t)r_img_stride(H, W) * 4);
     const size_t o_f0 = take(P * 2 * N * 8), o_f1 = take(P * 2 * N * 8), o_f2 = take(P * 2 * N * 8);
+    const size_t o_tab = take(2 * ((size_t)H + W) * 4);
     Workspace ws{};
     char* b = reinterpret_cast<char*>(base);
     ws.tmp = reinterpret_cast<float*>(b + o_tmp);
@@ -77,6 +79,7 @@ static Workspace carve(void* base, int n_pairs, int H, int W, const LevelPlan& l
     ws.flow[0] = reinterpret_cast<float*>(b + o_f0);
     ws.flow[1] = reinterpret_cast<float*>(b + o_f1);
     ws.flow[2] = reinterpret_cast<float*>(b + o_f2);
+    ws.tab = reinterpret_cast<int*>(b + o_tab);
     // tail pad: the staged (bulk-copy) rows of the iteration kernel are rounded up to 16-byte granules and may read a
     // few bytes past the last flow row
     ws.total = off + 256;
@@ -200,21 +203,34 @@ extern "C" int tf_farneback_pairs(const uint8_t* q0, const uint8_t* q1, float* f
         const long long rs = r_img_stride(h, w);
         rc = launch_polyexp(ws.I, ws.R, rs, 2 * n_pairs, h, w, pc, s);
         if (rc != TF_OK) return rc;
-        // initial flow: zeros at the coarsest level, else resize(prev) * (1 / pyr_scale)
+        // initial flow: zeros at the coarsest level, else resize(prev) * (1 / pyr_scale) -- formed inside the first
+        // iteration from the previous level's result (UpArgs) when the default kernel runs, else by its own kernel
         float* f_in = ws.flow[cur];
-        rc = launch_flow_upsample(prev_flow, f_in, 2 * n_pairs, ph, pw, h, w, (float)(1.0 / p->pyr_scale), s);
+        const bool fuse_up = prev_flow != nullptr && fb_iteration_can_fuse_upsample();
+        UpArgs up{};
+        if (fuse_up) {
+            up.coarse = prev_flow;
+            up.x0 = ws.tab; up.fx = reinterpret_cast<float*>(ws.tab + W);
+            up.y0 = ws.tab + 2 * W; up.fy = reinterpret_cast<float*>(ws.tab + 2 * W + H);
+            up.sh = ph; up.sw = pw; up.mul = (float)(1.0 / p->pyr_scale);
+            rc = launch_resize_tables(ws.tab, reinterpret_cast<float*>(ws.tab + W), w, pw, ws.tab + 2 * W,
+                                      reinterpret_cast<float*>(ws.tab + 2 * W + H), h, ph, s);
+        } else {
+            rc = launch_flow_upsample(prev_flow, f_in, 2 * n_pairs, ph, pw, h, w, (float)(1.0 / p->pyr_scale), s);
+        }
         if (rc != TF_OK) return rc;
         float* f_a = f_in;
         float* f_b = ws.flow[(cur + 1) % 3];
         const long long lvl_stride = (long long)2 * h * w * 2;  // [pair] stride of the (P, 2, h, w, 2) buffers
         for (int it = 0; it < p->num_iters; ++it) {
             const bool final_write = last_level && it == p->num_iters - 1;
+            const UpArgs* upp = (fuse_up && it == 0) ? &up : nullptr;
             if (final_write) {
                 rc = launch_fb_iteration(ws.R, rs, f_a, fwd, fwd_stride, bwd, bwd_stride, n_pairs, h, w, p->win_size,
-                                         p->max_value, last_level, s);
+                                         p->max_value, last_level, s, upp);
             } else {
                 rc = launch_fb_iteration(ws.R, rs, f_a, f_b, lvl_stride, f_b + (long long)h * w * 2, lvl_stride, n_pairs, h, w,
-                                         p->win_size, 0.f, last_level, s);
+                                         p->win_size, 0.f, last_level, s, upp);
             }
             if (rc != TF_OK) return rc;
             float* t = f_a; f_a = f_b; f_b = t;

@@ -30,12 +30,30 @@ inline long long r_img_stride(int h, int w) { return ((long long)5 * h * w + 3) 
 int launch_polyexp(const float* I, float* R, long long img_stride, int n_img, int h, int w, const PolyConsts& pc,
                    cudaStream_t s);
 
+// The flow up-sampling of a level fused into its first iteration (the default kernel only): instead of reading the level's
+// initial flow, the kernel forms it from the previous (coarser) level's result with cv::resize's bilinear weights.
+//   coarse (n_pairs, 2, sh, sw, 2); x0 / fx (w entries) and y0 / fy (h entries): first source index and weight of the
+//   second one per destination column / row (launch_resize_tables); mul = 1 / pyr_scale
+struct UpArgs {
+    const float* coarse;
+    const int* x0;
+    const float* fx;
+    const int* y0;
+    const float* fy;
+    int sh, sw;
+    float mul;
+};
+int launch_resize_tables(int* x0, float* fx, int w, int sw, int* y0, float* fy, int h, int sh, cudaStream_t s);
+bool fb_iteration_can_fuse_upsample();
+
 // One Jacobi iteration (UpdateMatrices + 13x13 box + 2x2 solve) for n_pairs x 2 directions.
 //   R          2*n_pairs images in the layout above: image 2p = prev, 2p+1 = next
 //   flow_in    (n_pairs, 2, h, w, 2)   [pair][direction]
 //   out_fwd/out_bwd + p*stride: where direction 0 / 1 results go (h, w, 2)
 //   clamp > 0: clamp results to +-clamp
+//   up != nullptr: flow_in is ignored, the initial flow is up-sampled from up->coarse inside the kernel
 int launch_fb_iteration(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride, float* out_bwd,
-                        long long bwd_stride, int n_pairs, int h, int w, int win, float clamp, bool full_res, cudaStream_t s);
+                        long long bwd_stride, int n_pairs, int h, int w, int win, float clamp, bool full_res, cudaStream_t s,
+                        const UpArgs* up = nullptr);
 
 }  // namespace tf

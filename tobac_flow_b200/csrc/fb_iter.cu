@@ -183,11 +183,13 @@ __device__ __forceinline__ void matrix_v3(const TapsV3& t, float4 c, float c4, f
 // WAL = 2: w % 4 == 0 -- every row of the 4-byte / 8-byte streams then starts at the same offset from a 16-byte
 // boundary, so the alignment skews of the staged rows are constants of the strip (hoisted) and the outputs can go out as
 // 16-byte stores.  WAL = 1: w even -- the same for the 8-byte streams (flow in, flow out) only.  WAL = 0: any w.
-template <int PF, int WAL>
+// UP = 1: the level's first iteration -- the initial flow is not read from flow_in but up-sampled from the previous level's
+// result (UpArgs) into the staging ring's flow rows by the CTA itself, a batch ahead like the bulk copies it replaces.
+template <int PF, int WAL, int UP>
 __global__ void __launch_bounds__(TsCfg::NT, 4)
 fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float* __restrict__ flow_in,
                   float* __restrict__ out_fwd, long long fwd_stride, float* __restrict__ out_bwd, long long bwd_stride,
-                  int h, int w, int chunk_rows, float clampv) {
+                  int h, int w, int chunk_rows, float clampv, UpArgs up) {
     using C = TsCfg;
     constexpr int NT = C::NT, HK = C::HK, ROWF = 5 * NT;         // a row of vertical sums: [A: NT x f2][B: NT x f2][C: NT]
     static_assert(PF == 1 || PF == 2, "rows of R1 taps in flight");
@@ -207,7 +209,8 @@ fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float
     const float* R0b = R0 + 4 * (long long)plane;
     const float4* R1a = reinterpret_cast<const float4*>(R1);
     const float* R1b = R1 + 4 * (long long)plane;
-    const float2* fin = reinterpret_cast<const float2*>(flow_in) + (long long)(2 * pair + dir) * plane;
+    const float2* fin = reinterpret_cast<const float2*>(flow_in) + (UP ? 0LL : (long long)(2 * pair + dir) * plane);
+    const float2* coarse = reinterpret_cast<const float2*>(up.coarse) + (UP ? (long long)(2 * pair + dir) * up.sh * up.sw : 0LL);
     float2* fout = reinterpret_cast<float2*>(dir ? out_bwd + (long long)pair * bwd_stride
                                                  : out_fwd + (long long)pair * fwd_stride);
     const int x0 = strip * C::OUT_W;
@@ -253,7 +256,7 @@ fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float
     const int swarp = tid >> 5, slane = tid & 31;
     const uint32_t bytes_a = (uint32_t)ncol * 16u, bytes_b = (((uint32_t)ncol + 6u) & ~3u) * 4u,
                    bytes_f = (((uint32_t)ncol + 2u) & ~1u) * 8u;
-    const uint32_t stage_tx = IT_RB * (bytes_a + bytes_b + bytes_f);
+    const uint32_t stage_tx = IT_RB * (bytes_a + bytes_b + (UP ? 0u : bytes_f));
     const char* st_base = slane == 0 ? reinterpret_cast<const char*>(R0a)
                         : (slane == 1 ? reinterpret_cast<const char*>(R0b) : reinterpret_cast<const char*>(fin));
     const int st_esz = slane == 0 ? 16 : (slane == 1 ? 4 : 8);
@@ -262,7 +265,7 @@ fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float
                                                  : (slane == 1 ? C::B_OFF + swarp * C::B_ROW : C::F_OFF + swarp * C::F_ROW));
     auto stage_batch = [&](int bb) {
         const uint32_t bar = smem_u32(&mbar[bb & 1]);
-        if (slane < 3) {
+        if (slane < (UP ? 2 : 3)) {
             const int y = row_y(IT_RB * bb + swarp);
             const uintptr_t src = (reinterpret_cast<uintptr_t>(st_base) + (long long)(y * w + cx0) * st_esz) & ~(uintptr_t)15;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -271,14 +274,35 @@ fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float
         if (tid == 0) mbar_arrive_expect_tx(&mbar[bb & 1], stage_tx);
     };
     const unsigned skb_c = (skb0 + (unsigned)cx0) & 3u, skf_c = (skf0 + (unsigned)cx0) & 1u;   // WA: the skews of every row
+    // UP: the four flow rows of batch bb, up-sampled from the coarse field, written by every thread for its own column
+    // (no alignment skew); called where the bulk copies of that batch are issued
+    auto upsample_batch = [&](int bb) {
+        const int x0 = __ldg(up.x0 + gx), x1 = min(x0 + 1, up.sw - 1);
+        const float fx = __ldg(up.fx + gx);
+#pragma unroll
+        for (int j = 0; j < IT_RB; ++j) {
+            const int y = row_y(IT_RB * bb + j);
+            const int y0 = __ldg(up.y0 + y), y1 = min(y0 + 1, up.sh - 1);
+            const float fy = __ldg(up.fy + y);
+            const float2* r0 = coarse + y0 * up.sw;
+            const float2* r1 = coarse + y1 * up.sw;
+            const float2 v = upsample_vec(__ldg(r0 + x0), __ldg(r0 + x1), __ldg(r1 + x0), __ldg(r1 + x1), fx, fy, up.mul);
+            reinterpret_cast<float2*>(ts_smem + (bb & 1) * C::SLOT_BYTES + C::F_OFF + j * C::F_ROW)[gxs] = v;
+        }
+    };
     auto staged_flow = [&](int bb, int j) {
-        unsigned sk = skf_c;
-        if (WAL == 0) sk = (skf0 + (unsigned)(row_y(IT_RB * bb + j) * w + cx0)) & 1u;
+        unsigned sk = UP ? 0u : skf_c;
+        if (WAL == 0 && !UP) sk = (skf0 + (unsigned)(row_y(IT_RB * bb + j) * w + cx0)) & 1u;
         return reinterpret_cast<const float2*>(ts_smem + (bb & 1) * C::SLOT_BYTES + C::F_OFF + j * C::F_ROW)[sk + gxs];
     };
 
     stage_batch(0);
     if (n_batches > 1) stage_batch(1);
+    if (UP) {
+        upsample_batch(0);
+        if (n_batches > 1) upsample_batch(1);
+        __syncthreads();
+    }
     mbar_wait(&mbar[0], 0u);
     TapsV3 S0, S1;
     issue_taps_v3(S0, R1a, R1b, w, h, gx, row_y(0), staged_flow(0, 0));
@@ -295,11 +319,11 @@ fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float
             const int y_cur = row_y(i);
             // R0 and the flow of this row from the staging ring
             const float4 c = reinterpret_cast<const float4*>(slot + C::A_OFF + j * C::A_ROW)[gx - xs];
-            unsigned skb = skb_c, skf = skf_c;
+            unsigned skb = skb_c, skf = UP ? 0u : skf_c;
             if (WAL < 2) {
                 const unsigned e_cur = (unsigned)(y_cur * w + cx0);
                 skb = (skb0 + e_cur) & 3u;
-                if (WAL == 0) skf = (skf0 + e_cur) & 1u;
+                if (WAL == 0 && !UP) skf = (skf0 + e_cur) & 1u;
             }
             const float c4 = reinterpret_cast<const float*>(slot + C::B_OFF + j * C::B_ROW)[skb + gxs];
             const float2 fcur = reinterpret_cast<const float2*>(slot + C::F_OFF + j * C::F_ROW)[skf + gxs];
@@ -342,7 +366,10 @@ fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float
         rb = (rb == 2) ? 0 : rb + 1;
         tm_wait_st();
         __syncthreads();
-        if (b + 2 < n_batches) stage_batch(b + 2);
+        if (b + 2 < n_batches) {
+            stage_batch(b + 2);
+            if (UP) upsample_batch(b + 2);     // (visible to its readers through the barriers of batches b + 1 / b + 2)
+        }
         // ---- H phase: a warp owns row hr of the batch, a lane four adjacent outputs ---------------------------------
         const int y = r_begin + b * IT_RB + hr - IT_HALO;
         if (y >= yc0 && y < yc1) {
@@ -423,11 +450,14 @@ fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_addr_s), "n"(C::TM_COLS) : "memory");
 }
 
-template <int PF>
+template <int PF, int UP>
 static void launch_v3_pf(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride,
-                         float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, float clamp, cudaStream_t s) {
+                         float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, float clamp, cudaStream_t s,
+                         const UpArgs* upp) {
     using C = TsCfg;
-    auto kern = (w & 3) == 0 ? fb_iter_v3_kernel<PF, 2> : ((w & 1) == 0 ? fb_iter_v3_kernel<PF, 1> : fb_iter_v3_kernel<PF, 0>);
+    auto kern = (w & 3) == 0 ? fb_iter_v3_kernel<PF, 2, UP> : ((w & 1) == 0 ? fb_iter_v3_kernel<PF, 1, UP> : fb_iter_v3_kernel<PF, 0, UP>);
+    UpArgs up{};
+    if (upp) up = *upp;
     // (the attribute is per device: set it on every call, it is cheap)
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     const int strips = cdiv(w, C::OUT_W);
@@ -436,41 +466,64 @@ static void launch_v3_pf(const float* R, long long img_stride, const float* flow
     for (int p0 = 0; p0 < n_pairs; p0 += 65535) {
         const int np = min(n_pairs - p0, 65535);
         dim3 g(2 * strips, chunks, np);
+        UpArgs upz = up;
+        if (UP) upz.coarse = up.coarse + (long long)(2 * p0) * 2 * up.sh * up.sw;
         kern<<<g, C::NT, C::SMEM_BYTES, s>>>(R + (long long)(2 * p0) * img_stride, img_stride,
-                                             flow_in + (long long)(2 * p0) * 2 * h * w, out_fwd + p0 * fwd_stride,
-                                             fwd_stride, out_bwd + p0 * bwd_stride, bwd_stride, h, w, chunk_rows, clamp);
+                                             UP ? nullptr : flow_in + (long long)(2 * p0) * 2 * h * w, out_fwd + p0 * fwd_stride,
+                                             fwd_stride, out_bwd + p0 * bwd_stride, bwd_stride, h, w, chunk_rows, clamp, upz);
     }
 }
 
 void launch_fb_v3(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride,
-                  float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, float clamp, int pf, cudaStream_t s) {
-    if (pf == 1) launch_v3_pf<1>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
-    else launch_v3_pf<2>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s);
+                  float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, float clamp, int pf, cudaStream_t s,
+                  const UpArgs* up) {
+    if (up) {
+        if (pf == 1) launch_v3_pf<1, 1>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s, up);
+        else launch_v3_pf<2, 1>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s, up);
+        return;
+    }
+    if (pf == 1) launch_v3_pf<1, 0>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s, nullptr);
+    else launch_v3_pf<2, 0>(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, s, nullptr);
 }
 
-// which iteration kernel runs: 3 = v3 with two rows of taps in flight (default), 4 = v3 with one, 0 = the scalar kernel
-// with its ring in shared memory, 1 = the scalar kernel with the ring in tensor memory.  TF_TMA in the environment sets
+// which iteration kernel runs: 3 = v3 with two rows of taps in flight (default), 4 = v3 with one, 5 = 3 with the flow
+// up-sampling in its own kernel instead of the first iteration, 0 = the scalar kernel with its ring in shared memory,
+// 1 = the scalar kernel with the ring in tensor memory.  TF_TMA in the environment sets
 // the initial choice; tf_fb_select_kernel changes it (A/B runs, cross-check tests).
 static int g_kernel_choice = -1;
 
+static int kernel_choice() {
+    if (g_kernel_choice < 0) {
+        const char* e = getenv("TF_TMA");
+        g_kernel_choice = e ? atoi(e) : 3;
+    }
+    return g_kernel_choice;
+}
+
+// the fused up-sampling exists in the default (v3) kernels only; TF_UPSAMPLE_FUSED=0 keeps the separate kernel (A/B)
+bool fb_iteration_can_fuse_upsample() {
+    static const char* e = getenv("TF_UPSAMPLE_FUSED");
+    if (e && atoi(e) == 0) return false;
+    const int k = kernel_choice();
+    return k != 0 && k != 1 && k != 5;
+}
+
 int launch_fb_iteration(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride,
                         float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, int win, float clamp,
-                        bool full_res, cudaStream_t s) {
+                        bool full_res, cudaStream_t s, const UpArgs* up) {
     if (win != IT_WIN) {
         set_error("fb iteration: only winSize 13 is built (got %d)", win);
         return TF_ERR_UNSUPPORTED;
     }
     if ((long long)h * w > 0x3fffffffLL) { set_error("fb iteration: level too large"); return TF_ERR_INVALID_ARGUMENT; }
     LaunchTimer lt(full_res ? KC_FB_ITER_L0 : KC_FB_ITER, 56.0 * h * w * 2 * n_pairs, s, cdiv(n_pairs, 65535));
-    if (g_kernel_choice < 0) {
-        const char* e = getenv("TF_TMA");
-        g_kernel_choice = e ? atoi(e) : 3;
-    }
-    switch (g_kernel_choice) {
+    const int choice = kernel_choice();
+    if (up && (choice == 0 || choice == 1)) { set_error("fb iteration: the scalar kernels have no fused up-sampling"); return TF_ERR_UNSUPPORTED; }
+    switch (choice) {
         case 0: launch_fb_scalar(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, false, s); break;
         case 1: launch_fb_scalar(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, true, s); break;
-        case 4: launch_fb_v3(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, 1, s); break;
-        default: launch_fb_v3(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, 2, s);
+        case 4: launch_fb_v3(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, 1, s, up); break;
+        default: launch_fb_v3(R, img_stride, flow_in, out_fwd, fwd_stride, out_bwd, bwd_stride, n_pairs, h, w, clamp, 2, s, up);
     }
     return check_launch("fb iteration");
 }
@@ -478,8 +531,8 @@ int launch_fb_iteration(const float* R, long long img_stride, const float* flow_
 }  // namespace tf
 
 extern "C" int tf_fb_select_kernel(int which) {
-    if (which != 0 && which != 1 && which != 3 && which != 4) {
-        tf::set_error("tf_fb_select_kernel: unknown kernel %d (0, 1: scalar; 3, 4: v3)", which);
+    if (which != 0 && which != 1 && which != 3 && which != 4 && which != 5) {
+        tf::set_error("tf_fb_select_kernel: unknown kernel %d (0, 1: scalar; 3, 4: v3; 5: v3 with the separate up-sampling kernel)", which);
         return TF_ERR_INVALID_ARGUMENT;
     }
     tf::g_kernel_choice = which;

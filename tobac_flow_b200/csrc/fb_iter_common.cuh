@@ -90,7 +90,17 @@ inline int plan_chunk_rows(int h, int strips, int n_pairs, long long slots, int*
 
 // the two kernels (selected in launch_fb_iteration)
 void launch_fb_v3(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride,
-                  float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, float clamp, int pf, cudaStream_t s);
+                  float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, float clamp, int pf, cudaStream_t s,
+                  const UpArgs* up);
+
+// cv::resize INTER_LINEAR of one flow vector from its four source vectors, times mul; shared by flow_upsample_kernel and by
+// the first iteration's fused up-sampling so that both give the same bits (explicit roundings, no contraction choices)
+__device__ __forceinline__ float lerp_rn(float a, float b, float f) { return fmaf(b, f, __fmul_rn(a, __fsub_rn(1.f, f))); }
+__device__ __forceinline__ float2 upsample_vec(float2 a, float2 b, float2 c, float2 d, float fx, float fy, float mul) {
+    const float ax = lerp_rn(a.x, b.x, fx), ay = lerp_rn(a.y, b.y, fx);
+    const float cx = lerp_rn(c.x, d.x, fx), cy = lerp_rn(c.y, d.y, fx);
+    return make_float2(__fmul_rn(lerp_rn(ax, cx, fy), mul), __fmul_rn(lerp_rn(ay, cy, fy), mul));
+}
 void launch_fb_scalar(const float* R, long long img_stride, const float* flow_in, float* out_fwd, long long fwd_stride,
                       float* out_bwd, long long bwd_stride, int n_pairs, int h, int w, float clamp, bool tmem_ring,
                       cudaStream_t s);

@@ -9,6 +9,7 @@
 
 #include "tf_common.cuh"
 #include "farneback_internal.cuh"
+#include "fb_iter_common.cuh"
 
 namespace tf {
 
@@ -662,11 +663,7 @@ __global__ void __launch_bounds__(256) blur_h_resize_kernel(const float* __restr
 // Two adjacent outputs per thread (one 16-byte store); the row coordinate is computed once per thread.
 __device__ __forceinline__ float2 upsample_one(const float2* __restrict__ r0, const float2* __restrict__ r1, int x0, int x1,
                                                float fx, float fy, float mul) {
-    const float2 a = r0[x0], b = r0[x1];
-    const float2 c = r1[x0], d = r1[x1];
-    const float ax = a.x * (1.f - fx) + b.x * fx, ay = a.y * (1.f - fx) + b.y * fx;
-    const float cx = c.x * (1.f - fx) + d.x * fx, cy = c.y * (1.f - fx) + d.y * fx;
-    return make_float2((ax * (1.f - fy) + cx * fy) * mul, (ay * (1.f - fy) + cy * fy) * mul);
+    return upsample_vec(r0[x0], r0[x1], r1[x0], r1[x1], fx, fy, mul);
 }
 
 // A block of 256 threads covers 512 columns x UP_ROWS rows of one field: cv::resize's double-precision source coordinates
@@ -865,6 +862,22 @@ int launch_pyramid_level(const uint8_t* q0, const uint8_t* q1, int n_pairs, int 
         }
     }
     return check_launch("pyramid level");
+}
+
+// cv::resize's source coordinates of a (sh, sw) -> (h, w) up-sampling, tabulated once per level for the first iteration's
+// fused up-sampling
+__global__ void resize_tables_kernel(int* __restrict__ x0, float* __restrict__ fx, int w, int sw, double scale_x,
+                                     int* __restrict__ y0, float* __restrict__ fy, int h, int sh, double scale_y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int a, b; float f;
+    if (i < w) { resize_coord(i, scale_x, sw, a, b, f); x0[i] = a; fx[i] = f; }
+    if (i < h) { resize_coord(i, scale_y, sh, a, b, f); y0[i] = a; fy[i] = f; }
+}
+
+int launch_resize_tables(int* x0, float* fx, int w, int sw, int* y0, float* fy, int h, int sh, cudaStream_t s) {
+    const int n = w > h ? w : h;
+    resize_tables_kernel<<<cdiv(n, 256), 256, 0, s>>>(x0, fx, w, sw, (double)sw / w, y0, fy, h, sh, (double)sh / h);
+    return check_launch("resize tables");
 }
 
 int launch_flow_upsample(const float* src, float* dst, int n_fields, int sh, int sw, int h, int w, float mul,
