@@ -14,7 +14,9 @@ is 288*N frames, time-sharded one day per rank with NCCL point-to-point halo exc
             input in pinned host memory and every result copied back to the host inside the timed region, on a
             bounded number of frames of the same shape.
 ``roofline`` the dominant kernel (the fused Farneback iteration at the full-resolution level): algorithmic bytes
-            (56 B per pixel-iteration) / its CUDA-event time measured live during the timed steps.
+            (56 B per pixel-iteration; the level's first iteration also forms its initial flow from the previous level's
+            result and carries the 10 B per pixel SURVEY 8d counts for that up-sampling) / its CUDA-event time measured
+            live during the timed steps.
 ``cpu_baseline`` the reference's CPU implementation of the same unit of work (OpenCV Farneback + cv2.remap through
             the oracle's restatement of the reference's Python) timed on this box's host cores on a bounded sample.
 

@@ -516,7 +516,11 @@ int launch_fb_iteration(const float* R, long long img_stride, const float* flow_
         return TF_ERR_UNSUPPORTED;
     }
     if ((long long)h * w > 0x3fffffffLL) { set_error("fb iteration: level too large"); return TF_ERR_INVALID_ARGUMENT; }
-    LaunchTimer lt(full_res ? KC_FB_ITER_L0 : KC_FB_ITER, 56.0 * h * w * 2 * n_pairs, s, cdiv(n_pairs, 65535));
+    // algorithmic bytes: 56 B per pixel-iteration; a first iteration that also up-samples its initial flow carries the
+    // bytes the separate up-sampling kernel accounts for (coarse field read, up-sampled field written: SURVEY 8d's 20 S term)
+    double bytes = 56.0 * h * w * 2 * n_pairs;
+    if (up) bytes += (8.0 * h * w + 8.0 * up->sh * up->sw) * 2 * n_pairs;
+    LaunchTimer lt(full_res ? KC_FB_ITER_L0 : KC_FB_ITER, bytes, s, cdiv(n_pairs, 65535));
     const int choice = kernel_choice();
     if (up && (choice == 0 || choice == 1)) { set_error("fb iteration: the scalar kernels have no fused up-sampling"); return TF_ERR_UNSUPPORTED; }
     switch (choice) {
