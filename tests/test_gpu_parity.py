@@ -554,6 +554,16 @@ def test_host_operators_overlapping_create_flow_equal_the_device_path(tfb, monke
             assert_same(a, b)
         assert_same(fh.forward_flow, want_f)
         assert_same(fh.backward_flow, want_b)
+    # an operand that is NOT the array the flow was made from (its device copy comes from another create_flow, whose
+    # upload is not ordered behind this flow's batch events): the operators must take the stream-ordered path
+    bt2 = (bt[::-1] * np.float32(0.5) + np.float32(100.0)).copy()
+    tflow.operand_cache_clear()
+    fa = tfb.create_flow(bt)
+    fb = tfb.create_flow(bt2)
+    assert fb._ready_frames != fa._ready_frames
+    got = fa.diff(bt2)
+    assert_same(got, fd.diff(torch.from_numpy(bt2).cuda()).cpu().numpy())
+    del fb
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -420,6 +420,7 @@ class Flow:
         # are final.  Work queued on the current stream is ordered behind all of them anyway; the host operators use the
         # events to start on the first frames (on the operator stream) while the later pairs are still being computed.
         self._ready = None
+        self._ready_frames = None      # data_ptr of the device copy of the frames those batches were computed from
         self._fwd_np = forward_flow if isinstance(forward_flow, np.ndarray) else None
         self._bwd_np = backward_flow if isinstance(backward_flow, np.ndarray) else None
         self._fwd_t = forward_flow if isinstance(forward_flow, torch.Tensor) else None
@@ -527,8 +528,8 @@ class Flow:
         # so results start to flow back over PCIe while the later pairs are in the iteration kernels.  Only taken when the
         # operand is the resident copy that create_flow uploaded (its upload events are behind the same batch events).
         ready = self._ready
-        if ready is not None and (resident is None or ready[-1][1].query()):
-            ready = None
+        if ready is not None and (resident is None or resident.data_ptr() != self._ready_frames or ready[-1][1].query()):
+            ready = None               # (another operand's upload is ordered on the current stream, not behind these events)
         s_k = _operator_stream(dev) if ready is not None else cur
 
         def wait_flow(b0):
@@ -904,7 +905,7 @@ def _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_meth
         # as "no clamp")
         fwd = torch.where(torch.isnan(fwd), fwd, torch.zeros_like(fwd))
         bwd = torch.where(torch.isnan(bwd), bwd, torch.zeros_like(bwd))
-    return fwd, bwd, ready
+    return fwd, bwd, (ready, frames.data_ptr()) if ready is not None else None
 
 
 def calculate_flow(data, model: str = "Farneback", vr_steps: int = 0, smoothing_passes: int = 0,
@@ -935,7 +936,8 @@ def create_flow(data, model: str = "Farneback", vr_steps: int = 0, smoothing_pas
     """
     fwd, bwd, ready = _calculate_flow_tensors(data, model, vr_steps, smoothing_passes, interp_method, "linear", max_value)
     flow = Flow(fwd, bwd)
-    flow._ready = ready
+    if ready is not None:
+        flow._ready, flow._ready_frames = ready
     return flow
 
 
