@@ -1,6 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-B="python bench.py --frames 8 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-detection"
-$B > /dev/null 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k regex:fb_iter_v3 -s 50 -c 2 -o gpurun_out/r2_prof_fb_v3_up -f $B > gpurun_out/ncu_fb_up.log 2>&1
-tail -2 gpurun_out/ncu_fb_up.log | cut -c1-200
+rm -f gpurun_out/ab.log
+V=$PWD/profiles/tools/_var/libtf_up2.so
+TF_LIB_PATH=$V timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "iteration or flow_small or three_levels or odd_sizes" > gpurun_out/r_tests.log 2>&1
+echo "rc $?" >> gpurun_out/r_tests.log; tail -2 gpurun_out/r_tests.log
+bash profiles/tools/ab.sh "TF_X=1" "TF_LIB_PATH=$V" "TF_X=1" "TF_LIB_PATH=$V" > /dev/null 2>&1
+grep -E "===|fps|fb_iter" gpurun_out/ab.log

@@ -278,16 +278,26 @@ fb_iter_v3_kernel(const float* __restrict__ R, long long img_stride, const float
     // (no alignment skew); called where the bulk copies of that batch are issued
     auto upsample_batch = [&](int bb) {
         const int x0 = __ldg(up.x0 + gx), x1 = min(x0 + 1, up.sw - 1);
-        const float fx = __ldg(up.fx + gx);
+        const float fx = __ldg(up.fx + gx), gxw = __fsub_rn(1.f, fx);
+        float2* dst = reinterpret_cast<float2*>(ts_smem + (bb & 1) * C::SLOT_BYTES + C::F_OFF) + gxs;
+        int y0_prev = -1;
+        float2 top = make_float2(0.f, 0.f), bot = top;           // the two source rows blended along x
 #pragma unroll
         for (int j = 0; j < IT_RB; ++j) {
             const int y = row_y(IT_RB * bb + j);
-            const int y0 = __ldg(up.y0 + y), y1 = min(y0 + 1, up.sh - 1);
+            const int y0 = __ldg(up.y0 + y);
             const float fy = __ldg(up.fy + y);
-            const float2* r0 = coarse + y0 * up.sw;
-            const float2* r1 = coarse + y1 * up.sw;
-            const float2 v = upsample_vec(__ldg(r0 + x0), __ldg(r0 + x1), __ldg(r1 + x0), __ldg(r1 + x1), fx, fy, up.mul);
-            reinterpret_cast<float2*>(ts_smem + (bb & 1) * C::SLOT_BYTES + C::F_OFF + j * C::F_ROW)[gxs] = v;
+            if (y0 != y0_prev) {                                 // (uniform: neighbouring rows often share their source rows)
+                const float2* r0 = coarse + y0 * up.sw;
+                const float2* r1 = coarse + min(y0 + 1, up.sh - 1) * up.sw;
+                const float2 a = __ldg(r0 + x0), b = __ldg(r0 + x1), c = __ldg(r1 + x0), d = __ldg(r1 + x1);
+                top = make_float2(fmaf(b.x, fx, __fmul_rn(a.x, gxw)), fmaf(b.y, fx, __fmul_rn(a.y, gxw)));
+                bot = make_float2(fmaf(d.x, fx, __fmul_rn(c.x, gxw)), fmaf(d.y, fx, __fmul_rn(c.y, gxw)));
+                y0_prev = y0;
+            }
+            const float gyw = __fsub_rn(1.f, fy);
+            dst[j * (C::F_ROW / 8)] = make_float2(__fmul_rn(fmaf(bot.x, fy, __fmul_rn(top.x, gyw)), up.mul),
+                                                  __fmul_rn(fmaf(bot.y, fy, __fmul_rn(top.y, gyw)), up.mul));
         }
     };
     auto staged_flow = [&](int bb, int j) {
