@@ -83,3 +83,33 @@ def test_blob_known_answers(golden):
     assert np.allclose(fwd[4, 50, 50], (0.10432175, 0.10432258), atol=2e-5)
     assert np.allclose(bwd[4, 50, 50], (-0.10804594, -0.10804673), atol=2e-5)
     assert np.allclose(fwd[0, 0, 0], (0.00212546, 0.00212546), atol=2e-5)
+
+
+@pytest.mark.parametrize("shape", [(300, 500), (129, 260), (97, 1100)])
+def test_combined_taps_equal_blur_then_resize(shape):
+    """The algebra behind the row / half pyramid kernels (csrc/pyramid.cu): GaussianBlur followed by the bilinear resize is
+    one separable filter per destination pixel with taps cw[c] = g[c] + f * (g[c - 1] - g[c]) (f = the resize weight of the
+    second source row / column, g[-1] = g[ksize] = 0), REFLECT_101 applied to the source index.  Checked here in float64
+    against the oracle's blur -> resize on every down-sampled level."""
+    H, W = shape
+    rng = np.random.default_rng(H * W)
+    img = rng.integers(0, 256, (H, W)).astype(np.uint8)
+    for lvl in fb.level_plan(H, W):
+        if (lvl["h"], lvl["w"]) == (H, W):
+            continue
+        g = fb.gaussian_kernel(lvl["ksize"], lvl["sigma"]).astype(np.float64)
+        ks, rad = lvl["ksize"], lvl["ksize"] // 2
+        gext = np.concatenate([g, [0.0]])                       # g[ksize] = 0
+        dg = np.concatenate([[0.0], g]) - gext                  # g[c - 1] - g[c]
+        y0, _, fy = fb._linear_coords(lvl["h"], H)
+        x0, _, fx = fb._linear_coords(lvl["w"], W)
+        src = img.astype(np.float64)
+        rows = fb._reflect101((y0[:, None] - rad) + np.arange(ks + 1)[None, :], H)          # (h, ks + 1)
+        cv = gext[None, :] + fy.astype(np.float64)[:, None] * dg[None, :]
+        V = np.einsum("jr,jrx->jx", cv, src[rows])                                           # vertical pass: (h, W)
+        cols = fb._reflect101((x0[:, None] - rad) + np.arange(ks + 1)[None, :], W)          # (w, ks + 1)
+        ch = gext[None, :] + fx.astype(np.float64)[:, None] * dg[None, :]
+        out = np.einsum("ic,jic->ji", ch, V[:, cols])
+        ref = fb.pyramid_level(img, lvl)
+        assert out.shape == ref.shape
+        assert np.abs(out - ref).max() <= 2e-4, (lvl["k"], np.abs(out - ref).max())
