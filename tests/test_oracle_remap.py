@@ -90,3 +90,28 @@ def test_lanczos_small_images_vs_cv2(shape):
     for fill in (np.nan, 0.0):
         ref = cv2.remap(src, np.stack([mapx, mapy], -1), None, cv2.INTER_LANCZOS4, None, cv2.BORDER_CONSTANT, fill)
         assert np.array_equal(ref, rm.remap(src, mapx, mapy, "lanczos", fill), equal_nan=True)
+
+
+def test_conversion_free_quantisation_identity():
+    """The identity behind `quantise_fast` (csrc/gather.cu): for a float32 position p with |32 p| < 2^22 the integer
+    cvRound(32 p) (round half to even) sits in the low mantissa bits of fl32(32 p + 1.5 * 2^23) -- 32 p is exact, so the
+    fused multiply-add rounds once, exactly as cvRound does; anything out of range, NaN or infinite yields a value that
+    fails the kernel's unsigned range test (q < limit <= 32767 * 32)."""
+    rng = np.random.default_rng(11)
+    p = np.concatenate([
+        rng.uniform(-100, 3000, 200000), rng.uniform(-1, 1, 50000),
+        (np.arange(-4000, 4000) + 0.5) / 32.0,                 # exact ties of the 1/32 grid
+        (np.arange(-4000, 4000) + 0.5) / 32.0 + 1e-6, np.array([0.0, -0.0, 131071.9, -131071.9, 5e-39, -5e-39]),
+    ]).astype(np.float32)
+
+    def quantise_fast(x):
+        r = (x.astype(np.float64) * 32.0 + 12582912.0).astype(np.float32)      # one rounding, like the FMA
+        return r.view(np.int32).astype(np.int64) - 0x4B400000
+
+    want = np.rint(p.astype(np.float64) * 32.0).astype(np.int64)               # 32 p is exact in float32 and float64
+    assert np.array_equal(quantise_fast(p), want)
+    limit = 32767 * 32
+    with np.errstate(all="ignore"):
+        bad = np.array([1.4e5, -1.4e5, 4.2e6, -4.2e6, 1e9, -1e9, 3e38, -3e38, np.inf, -np.inf, np.nan], np.float32)
+        q = quantise_fast(bad) & 0xFFFFFFFF                                     # the kernel compares as unsigned
+    assert (q >= limit).all()
