@@ -1,6 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-B="python bench.py --frames 8 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-detection"
-$B > /dev/null 2>&1 || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"fb_iter|sl_gather|sl_lean|sobel_lin|pyr_|blur|polyexp|flow_upsample|resize_tables|pair_|minmax|finalise" -c 400 --csv --log-file gpurun_out/launches_r2_final.csv $B > gpurun_out/ncu_launches_final.log 2>&1
-tail -1 gpurun_out/ncu_launches_final.log | cut -c1-100
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_detection.py -x -q -m gpu > gpurun_out/u_tests.log 2>&1
+echo "rc $?" >> gpurun_out/u_tests.log; tail -2 gpurun_out/u_tests.log
+python profiles/tools/gather_time.py 2>&1 | grep "nans=True"
