@@ -1,5 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_detection.py -x -q -m gpu > gpurun_out/u_tests.log 2>&1
-echo "rc $?" >> gpurun_out/u_tests.log; tail -2 gpurun_out/u_tests.log
-python profiles/tools/gather_time.py 2>&1 | grep "nans=True"
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r2_last.json 2> gpurun_out/bench_r2_last.err
+echo "bench rc $?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_r2_last.json').read().strip().splitlines()[-1])
+r=d['roofline']
+print('value',round(d['value'],1),'ms',round(d['ms_per_step'],1),'whole',round(r['whole_step']['frac'],4),'dom',round(r['frac'],4),'e2e',round(d['e2e']['value'],1),'launches',d['gpu_launches'], d['clocks']['sm_mhz'])
+PY
